@@ -1,0 +1,170 @@
+"""Generate tests/golden/*.npz by RUNNING THE UNMODIFIED REFERENCE (read-only at /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no /root/reference):
+
+    python oracle/make_golden.py
+
+The reference imports matplotlib at import time; `oracle/mpl_stub` satisfies the import, nothing plots.
+Every fixture stores the inputs (parameters, seed, exported random coefficients) next to the reference's
+outputs so that the tests can (a) pin `oracle/splitstep.py` against the reference and (b) feed the same
+coefficients to the CUDA path.  Versions are recorded in each file (`versions`).
+"""
+from __future__ import annotations
+
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("PYATM_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    sys.path.insert(0, os.path.join(HERE, "mpl_stub"))
+    warnings.simplefilter("ignore", SyntaxWarning)
+    import pyatmosphere  # noqa: F401  (the reference)
+    return pyatmosphere
+
+
+def _versions():
+    import scipy
+    return np.array([f"numpy {np.__version__}", f"scipy {scipy.__version__}"])
+
+
+def build_channel(pa, p):
+    return pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]),
+        source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=p.get("F0", np.inf)),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.SSPhaseScreen(
+                model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
+                f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])),
+            length=p["length"], count=p["count"], position_in_slab=p.get("where", "middle"),
+            losses_db=p.get("losses_db", 0)),
+        pupil=pa.CirclePupil(radius=p["pupil"]),
+    )
+
+
+def export_realization(pa, ch, seed):
+    """Replays the reference's draw order screen by screen, then re-seeds and runs the reference itself."""
+    ch.path.init_phase_screens()
+    np.random.seed(seed)
+    rho, theta, value = [], [], []
+    for ps in ch.path.phase_screens:
+        sp = ps._get_spectrum(False)
+        rho.append(np.asarray(sp.rho)); theta.append(np.asarray(sp.theta)); value.append(np.asarray(sp.value))
+    psd = np.asarray(ch.path.phase_screens[0]._get_psd())
+    np.random.seed(seed)
+    legs = []
+    gen = ch.generator(pupil=False, store_output=True)
+    screens = []
+    for u, phi in gen:
+        legs.append(np.asarray(u)); screens.append(np.asarray(phi))
+    out = np.asarray(ch.output)
+    np.random.seed(seed)
+    out_run = np.asarray(ch.run(pupil=False))
+    # Channel.generator stores the generator's return value (part losses only, pathes.py:71-75) while
+    # Channel.run goes through AbstractPath.output, which applies the full dB loss once more (pathes.py:23-24).
+    return dict(rho=np.stack(rho), theta=np.stack(theta), value=np.stack(value), psd=psd,
+                screens=np.stack(screens), legs=np.stack(legs), field=out_run, field_generator=out)
+
+
+def measures_of(pa, ch, out):
+    m = pa.measures
+    names = ["eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2"]
+    vals = [getattr(m, k)(ch, output=out) for k in names]
+    eta_pupil = m.eta(ch, output=ch.pupil.output(out))
+    return np.array(vals + [eta_pupil], dtype=np.float64)
+
+
+def params_arrays(p):
+    keys = sorted(p)
+    return dict(param_keys=np.array(keys), param_vals=np.array([str(p[k]) for k in keys]))
+
+
+def case_vacuum(pa):
+    """Restated tests/itest_vacuum_propagation.ipynb cells 3-7 on the current reference tree."""
+    n, delta, wvl, w0, length = 256, 2e-3, 809e-9, 2e-2, 4e3
+    ch = pa.Channel(grid=pa.RectGrid(resolution=n, delta=delta),
+                    source=pa.GaussianSource(wvl=wvl, w0=w0, F0=np.inf),
+                    path=pa.pathes.VacuumPath(length=length), pupil=pa.CirclePupil(radius=1.0))
+    src = np.asarray(ch.source.output())
+    out = np.asarray(ch.run(pupil=False))
+    m = measures_of(pa, ch, out)
+    np.savez_compressed(os.path.join(OUT, "vacuum256.npz"), n=n, delta=delta, wvl=wvl, w0=w0, length=length,
+                        source=src.astype(np.complex128), field=out, measures=m,
+                        abs_sum=np.abs(out.sum()) * delta**2, versions=_versions())
+
+
+def case_turbulent(pa, name, p, seed, with_legs=True):
+    ch = build_channel(pa, p)
+    r = export_realization(pa, ch, seed)
+    m = measures_of(pa, ch, r["field"])
+    extra = {}
+    if with_legs:
+        extra = dict(screens=r["screens"], legs=r["legs"])
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), seed=seed, rho=r["rho"], theta=r["theta"],
+                        value=r["value"], psd=r["psd"], field=r["field"], field_generator=r["field_generator"],
+                        measures=m,
+                        positions=np.asarray(ch.path.positions), versions=_versions(), **params_arrays(p),
+                        **extra)
+
+
+def case_psd(pa):
+    """Ring PSDs of the two README channels (independent of the spatial grid)."""
+    c1 = dict(n=64, delta=1e-3, wvl=808e-9, w0=0.09, Cn2=1e-15, l0=3e-3, L0=1e3, m=2**10,
+              f_min=1 / 1e3 / 15, f_max=1 / 3e-3 * 2, length=10e3, count=5, pupil=0.12)
+    c3 = dict(n=64, delta=1.5e-3, wvl=808e-9, w0=0.12, Cn2=5e-16, l0=6e-3, L0=1e3, m=2**10,
+              f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2, length=50e3, count=5, pupil=0.2)
+    out = {}
+    for tag, p in (("c1", c1), ("c3", c3)):
+        ch = build_channel(pa, p)
+        ch.path.init_phase_screens()
+        ps = ch.path.phase_screens[0]
+        out[tag + "_psd"] = np.asarray(ps._get_psd())
+        out[tag + "_base"] = np.asarray(ps.f_grid.base)
+        out[tag + "_rytov2"] = ch.get_rythov2()
+    np.savez_compressed(os.path.join(OUT, "psd_readme.npz"), versions=_versions(), **out)
+
+
+def case_simulation(pa, p, seed, count):
+    """Per-realization scalar tables of BeamResult + PDTResult from the reference's Simulation loop."""
+    ch = build_channel(pa, p)
+    beam = pa.simulations.BeamResult(ch, max_size=count)
+    pdt = pa.simulations.PDTResult(ch, max_size=count)
+    sim = pa.simulations.Simulation([beam, pdt])
+    np.random.seed(seed)
+    sim.run()
+    table = np.array([mm.data for mm in beam.measures] + [pdt.measures[0].data], dtype=np.float64).T
+    names = np.array([mm.name for mm in beam.measures] + [pdt.measures[0].name])
+    stats = np.array([beam.bw, beam.lt, beam.st], dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "simulation128.npz"), seed=seed, table=table, names=names,
+                        stats=stats, versions=_versions(), **params_arrays(p))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    pa = _import_reference()
+    case_vacuum(pa)
+    case_psd(pa)
+    small = dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, m=96,
+                 f_min=1 / 1e2 / 15, f_max=1 / 8e-3, length=6e3, count=3, pupil=0.1)
+    case_turbulent(pa, "turb128", small, seed=1234)
+    lossy = dict(small, where="after", losses_db=1.5, count=2, F0=4e3, m=64)
+    case_turbulent(pa, "turb128_after_lossy", lossy, seed=7)
+    before = dict(small, where="before", count=2, m=64, n=64, delta=6e-3)
+    case_turbulent(pa, "turb64_before", before, seed=99)
+    quick = dict(n=256, delta=1e-3 * 4, wvl=808e-9, w0=0.09, Cn2=1e-15, l0=3e-3, L0=1e3, m=2**10,
+                 f_min=1 / 1e3 / 15, f_max=1 / 3e-3 * 2, length=10e3, count=5, pupil=0.12)
+    case_turbulent(pa, "quick256", quick, seed=5, with_legs=False)
+    case_simulation(pa, small, seed=2024, count=6)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

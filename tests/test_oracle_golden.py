@@ -1,0 +1,182 @@
+"""Pins oracle/splitstep.py against fixtures produced by running the unmodified reference
+(oracle/make_golden.py) and against the reference's own vacuum-propagation asserts
+(tests/itest_vacuum_propagation.ipynb cells 3-7, restated).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_l2
+from oracle import splitstep as orc
+
+TURB = ["turb128", "turb128_after_lossy", "turb64_before", "quick256"]
+
+
+def _axes(p):
+    return orc.rect_xy(p["n"], p["delta"])
+
+
+def _redraw(g):
+    p = g["params"]
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    np.random.seed(int(g["seed"]))
+    return [orc.draw_spectrum(base, g["psd"]) for _ in range(p["count"])]
+
+
+@pytest.mark.parametrize("tag", ["c1", "c3"])
+def test_ring_psd_matches_reference(tag):
+    g = load_golden("psd_readme")
+    par = dict(c1=dict(Cn2=1e-15, l0=3e-3, L0=1e3, wvl=808e-9, thickness=10e3 / 5, f_min=1 / 1e3 / 15, f_max=1 / 3e-3 * 2),
+               c3=dict(Cn2=5e-16, l0=6e-3, L0=1e3, wvl=808e-9, thickness=50e3 / 5, f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2))[tag]
+    base = orc.logpolar_base(2**10, par["f_min"], par["f_max"])
+    assert np.array_equal(base, g[tag + "_base"])
+    psd = orc.ring_psd(base, par["Cn2"], par["l0"], par["L0"], par["wvl"], par["thickness"])
+    assert psd.dtype == np.float32
+    assert np.array_equal(psd, g[tag + "_psd"])
+
+
+def test_rytov_readme_value():
+    g = load_golden("psd_readme")
+    k = 2 * np.pi / 808e-9
+    assert orc.rytov2(5e-16, k, 50e3) == pytest.approx(float(g["c3_rytov2"]), rel=1e-14)
+    assert orc.rytov2(5e-16, k, 50e3) == pytest.approx(27.7, abs=0.05)      # main.ipynb:184
+
+
+@pytest.mark.parametrize("name", TURB)
+def test_draw_order_and_values(name):
+    g = load_golden(name)
+    p = g["params"]
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    psd = orc.ring_psd(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+    assert np.array_equal(psd, g["psd"])
+    for s, (rho, theta, value) in enumerate(_redraw(g)):
+        assert rho.dtype == np.float32 and theta.dtype == np.float32 and value.dtype == np.complex64
+        assert np.array_equal(rho, g["rho"][s])
+        assert np.array_equal(theta, g["theta"][s])
+        assert np.array_equal(value, g["value"][s])
+
+
+@pytest.mark.parametrize("name", ["turb128", "turb128_after_lossy", "turb64_before"])
+def test_screens_ref_mode_equal_reference(name):
+    g = load_golden(name)
+    x, y = _axes(g["params"])
+    for s in range(g["params"]["count"]):
+        fx, fy = orc.spectrum_to_fxy(g["rho"][s], g["theta"][s])
+        phi = orc.ss_screen(x, y, fx, fy, g["value"][s], mode="ref")
+        assert phi.dtype == np.float32
+        # same BLAS, same operation order: agreement to float32 rounding of a sum of magnitude |phi|
+        assert np.max(np.abs(phi - g["screens"][s])) <= 2e-6 * np.max(np.abs(phi)) + 1e-6
+        phi64 = orc.ss_screen(x, y, fx, fy, g["value"][s], mode="f64")
+        # the reference's own complex64 evaluation sits ~1e-4 rad from the float64 evaluation
+        assert np.max(np.abs(phi64 - g["screens"][s])) < 5e-3
+
+
+@pytest.mark.parametrize("name", TURB)
+def test_propagate_ref_mode_equals_reference(name):
+    g = load_golden(name)
+    p = g["params"]
+    x, y = _axes(p)
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], p.get("F0", np.inf), mode="ref")
+    screens = []
+    for s in range(p["count"]):
+        fx, fy = orc.spectrum_to_fxy(g["rho"][s], g["theta"][s])
+        screens.append(orc.ss_screen(x, y, fx, fy, g["value"][s], mode="ref"))
+    pos = orc.screen_positions(p["length"], p["count"], p.get("where", "middle"))
+    assert np.allclose(pos, g["positions"], rtol=0, atol=0)
+    kw = dict(length=p["length"], positions=pos, wvl=p["wvl"], delta=p["delta"], losses_db=p.get("losses_db", 0))
+    out = orc.propagate(u0, screens, mode="ref", **kw)
+    assert out.dtype == g["field"].dtype      # complex64, or complex128 when a float64 loss share promotes it
+    assert rel_l2(out, g["field"]) < 2e-6
+    gen = orc.propagate(u0, screens, mode="ref", through_output=False, **kw)
+    assert rel_l2(gen, g["field_generator"]) < 2e-6
+    if "legs" in g:
+        _, legs = orc.propagate(u0, g["screens"], mode="ref", keep_legs=True, **kw)
+        for a, b in zip(legs, g["legs"]):
+            assert rel_l2(a, b) < 2e-6
+    # float64 restatement: differs from the reference only by the reference's own complex64 screen error
+    s64 = []
+    for s in range(p["count"]):
+        fx, fy = orc.spectrum_to_fxy(g["rho"][s], g["theta"][s])
+        s64.append(orc.ss_screen(x, y, fx, fy, g["value"][s], mode="f64"))
+    u64 = orc.gaussian_source(x, y, p["w0"], p["wvl"], p.get("F0", np.inf), mode="f64")
+    out64 = orc.propagate(u64, s64, mode="f64", **kw)
+    assert out64.dtype == np.complex128
+    assert rel_l2(out64, g["field"]) < 5e-3
+
+
+@pytest.mark.parametrize("name", TURB)
+def test_measures_ref_mode(name):
+    g = load_golden(name)
+    p = g["params"]
+    x, y = _axes(p)
+    m = orc.moments(g["field"], x, y, p["delta"], pupils=[(p["pupil"], (0, 0))], mode="ref")
+    got = [m["eta"], m["mean_x"], m["mean_y"], m["mean_x2"], m["mean_xy"], m["mean_y2"], m["eta_pupil"][0]]
+    assert np.allclose(got, g["measures"], rtol=1e-6, atol=1e-9)
+    m64 = orc.moments(g["field"], x, y, p["delta"], pupils=[(p["pupil"], (0, 0))], mode="f64")
+    got64 = [m64["eta"], m64["mean_x"], m64["mean_y"], m64["mean_x2"], m64["mean_xy"], m64["mean_y2"], m64["eta_pupil"][0]]
+    assert np.allclose(got64, g["measures"], rtol=2e-5, atol=2e-7)
+    # closed form of BeamResult.mean_x2_r from the five moments
+    r0 = np.hypot(m64["mean_x"], m64["mean_y"])
+    c, s = m64["mean_x"] / r0, m64["mean_y"] / r0
+    closed = c * c * m64["mean_x2"] + 2 * c * s * m64["mean_xy"] + s * s * m64["mean_y2"]
+    assert closed == pytest.approx(m64["mean_x2_r"], rel=1e-9)
+
+
+def test_vacuum_notebook_asserts():
+    """tests/itest_vacuum_propagation.ipynb cells 3-7: 256^2, delta=2 mm, 809 nm, w0=2 cm, 4 km."""
+    g = load_golden("vacuum256")
+    n, delta, wvl, w0, length = int(g["n"]), float(g["delta"]), float(g["wvl"]), float(g["w0"]), float(g["length"])
+    x, y = orc.rect_xy(n, delta)
+    for mode in ("ref", "f64"):
+        u0 = orc.gaussian_source(x, y, w0, wvl, mode=mode)
+        if mode == "ref":
+            assert rel_l2(u0, g["source"]) < 1e-12
+        out = orc.vacuum_leg(u0, length, wvl, delta, mode=mode)
+        assert rel_l2(out, g["field"]) < 3e-7
+        m = orc.moments(out, x, y, delta, pupils=[(1.0, (0, 0))], mode="f64")
+        assert m["eta_pupil"][0] == pytest.approx(1.0, abs=1e-6)                      # eta == 1 (6 dp)
+        assert abs(out.astype(np.complex128).sum()) * delta**2 == pytest.approx(np.sqrt(2 * np.pi) * w0, abs=1e-7)
+        assert m["eta"] == pytest.approx(1.0, abs=1e-5)
+        w = np.sqrt(2 * (m["mean_x2"] + m["mean_y2"]))
+        assert w == pytest.approx(orc.gaussian_width(w0, wvl, np.inf, length), abs=1e-7)
+        ana = orc.analytic_gaussian_field(x, y, w0, wvl, length)
+        assert rel_l2(out, ana) < 5e-7
+
+
+def test_simulation_table_replay():
+    """Replays the reference Simulation([BeamResult, PDTResult]) loop with the oracle: same seed, same
+    per-realization scalars (simulations/simulation.py:89-114, beam.py:16-33, pdt.py:15-26)."""
+    g = load_golden("simulation128")
+    p = g["params"]
+    x, y = _axes(p)
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    psd = orc.ring_psd(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+    pos = orc.screen_positions(p["length"], p["count"])
+    np.random.seed(int(g["seed"]))
+    rows = []
+    for _ in range(g["table"].shape[0]):
+        u = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="ref")
+        screens = []
+        for s in range(p["count"]):
+            rho, theta, value = orc.draw_spectrum(base, psd)
+            fx, fy = orc.spectrum_to_fxy(rho, theta)
+            screens.append(orc.ss_screen(x, y, fx, fy, value, mode="ref"))
+        out = orc.propagate(u, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", through_output=False)
+        m = orc.moments(out, x, y, p["delta"], pupils=[(p["pupil"], (0, 0))], mode="ref")
+        rows.append([m["mean_x"], m["mean_y"], m["mean_x2"], m["mean_xy"], m["mean_y2"], m["mean_x2_r"], m["eta_pupil"][0]])
+    assert list(g["names"]) == ["mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2", "mean_x2_r", str(p["pupil"])]
+    assert np.allclose(np.array(rows), g["table"], rtol=2e-5, atol=1e-8)
+    st = orc.beam_statistics(g["table"][:, 0], g["table"][:, 2])
+    assert np.allclose([st["bw"], st["lt"], st["st"]], g["stats"], rtol=1e-12)
+
+
+def test_positions_and_legs():
+    assert np.allclose(orc.screen_positions(50e3, 5, "middle"), [5e3, 15e3, 25e3, 35e3, 45e3])
+    assert np.allclose(orc.leg_lengths(50e3, orc.screen_positions(50e3, 5)), [5e3, 1e4, 1e4, 1e4, 1e4, 5e3])
+    assert orc.leg_lengths(10.0, orc.screen_positions(10.0, 2, "before")) == [0.0, 5.0, 5.0]
+    assert orc.leg_lengths(10.0, orc.screen_positions(10.0, 2, "after")) == [5.0, 5.0, 0.0]
+    with pytest.raises(ValueError):
+        orc.screen_positions(1.0, 2, "centre")
+
+
+def test_histogram_convention():
+    h = orc.pdt_histogram([0.0, 0.004999, 0.005, 1.0, 1.2, -0.1, 0.9999], bins=200)
+    assert h.sum() == 5 and h[0] == 2 and h[1] == 1 and h[199] == 2
