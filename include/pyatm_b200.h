@@ -1,0 +1,155 @@
+/* pyatm_b200.h -- C ABI of libpyatm_b200.so: hand-written sm_100a kernels for the Monte-Carlo split-step
+ * beam-propagation hot path of KlenM/pyAtmosphere.
+ *
+ * This is the drop-in boundary: the reference reaches its array backend through
+ * pyatmosphere/gpu.py:9-20 (`get_xp()` -> cupy, `get_array()`); every function below replaces the cupy calls
+ * one reference function makes (file:line given per entry, relative to /root/reference/pyatmosphere/).
+ * The Python host (pyatmosphere_b200/_native.py) binds exactly these symbols with ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; pa_last_error() gives the text (thread local).
+ *  - no exceptions, no Python or torch types: plain pointers, sizes and doubles only.
+ *  - pointers named *_dev are device pointers owned by the caller (torch tensors on the Python side),
+ *    pointers named *_host are host pointers.  The library never frees caller memory.
+ *  - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it unless stated otherwise.
+ *  - fields are [batch][N][N] row-major (row index <-> y, column index <-> x, grids.py:57-69), complex64
+ *    (precision PA_C64) or complex128 (PA_C128), interleaved re/im.
+ *  - a pa_ctx belongs to one device and one thread at a time (the reference is single-threaded too).
+ */
+#ifndef PYATM_B200_H
+#define PYATM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PA_VERSION 100
+#define PA_C64 0
+#define PA_C128 1
+
+/* screen synthesis methods */
+#define PA_SCREEN_EXACT 0   /* float64 CUDA-core contraction (+ float64 polynomial for the low rings) */
+#define PA_SCREEN_TC 1      /* tcgen05 split-fp16 tensor-core contraction (+ float64 polynomial) */
+
+#define PA_MEASURE_HEAD 8   /* eta, mean_x, mean_y, mean_x2, mean_xy, mean_y2, mean_x2_r, 0 */
+#define PA_MAX_PUPILS 8     /* apertures evaluated per pa_measure call */
+
+#if defined(__GNUC__)
+#define PA_API __attribute__((visibility("default")))
+#else
+#define PA_API
+#endif
+
+typedef struct pa_ctx pa_ctx;
+
+PA_API int pa_version(void);
+PA_API const char* pa_last_error(void);
+PA_API int pa_device_count(int* count);
+
+/* ---- context ------------------------------------------------------------------------------------------
+ * replaces gpu.py:9-14 (backend selection) and the per-call rebuilding of grids (grids.py:63-85): twiddle
+ * tables, permuted transfer-function tables and workspace live here. n: power of two in [64, 8192]. */
+PA_API int pa_ctx_create(pa_ctx** ctx, int device, int n, int precision);
+PA_API int pa_ctx_destroy(pa_ctx* ctx);
+/* grids.py:63-72 RectGrid.get_x/get_y: the float32 axes exactly as numpy builds them, uploaded once. */
+PA_API int pa_ctx_set_axes(pa_ctx* ctx, const float* x_host, const float* y_host, double delta);
+/* frequency (numpy fft order index q in [0,N)) held at storage position p of a permuted spectrum */
+PA_API int pa_ctx_permutation(pa_ctx* ctx, int* perm_host);
+/* launch geometry of the two FFT passes: {rows threads, rows per CTA, rows smem, cols threads, cols per CTA, cols smem} */
+PA_API int pa_ctx_fft_geometry(pa_ctx* ctx, int* six_ints_host);
+
+/* ---- building blocks (one per reference function) --------------------------------------------------------*/
+/* sources.py:21-23 GaussianSource.output -> theory/sources.py:16-18 GaussianBeam.amplitude */
+PA_API int pa_source_gaussian(pa_ctx* ctx, void* field_dev, int batch, double w0, double wvl, double F0, void* stream);
+
+/* pathes.py:27-40 VacuumPath.lossless_output -> theory/vacuum.py:5-7 -> utils.py:42-50 (fft2/ifft2).
+ * In place, natural order in and out; length <= 0 leaves the field untouched. */
+PA_API int pa_vacuum_leg(pa_ctx* ctx, void* field_dev, int batch, double length, double wvl, void* stream);
+
+/* phase_screens.py:108-136 SSPhaseScreen.generate_phase_screen (real part, :25-28).
+ * fx, fy: [nscreens][m] float32; coef: [nscreens][m] complex64 (interleaved); rings sorted by radius.
+ * m_split / degree: rings below m_split are summed as a float64 polynomial of that total degree
+ * (m_split = 0, degree = -1: every ring goes through the contraction).
+ * turns_dev: [nscreens][N][N] phase/2pi reduced to [-0.5,0.5], float32 (PA_C64 ctx) or float64 (PA_C128);
+ * phi_dev (optional): full phase in radians, float32 or float64 (phi_f64). */
+PA_API int pa_screen_ss(pa_ctx* ctx, const float* fx_dev, const float* fy_dev, const float* coef_dev, int m, int m_split,
+                 int degree, double shift_x, double shift_y, int nscreens, void* turns_dev, void* phi_dev,
+                 int phi_f64, int method, void* stream);
+
+/* pathes.py:72-73  u <- scale * exp(-i phi) * u  with phi given in turns (see pa_phase_to_turns) */
+PA_API int pa_apply_screen(pa_ctx* ctx, void* field_dev, int batch, const void* turns_dev, double scale, void* stream);
+PA_API int pa_phase_to_turns(pa_ctx* ctx, const void* phi_dev, int phi_f64, void* turns_dev, size_t count, void* stream);
+
+/* measures.py:1-4 I = |u|^2 (float32 / float64 out) */
+PA_API int pa_intensity(pa_ctx* ctx, const void* field_dev, void* out_dev, int batch, void* stream);
+/* pupils.py:8-13 CirclePupil.output: out = in * [(x-sx)^2 + (y+sy)^2 <= r^2] */
+PA_API int pa_pupil_apply(pa_ctx* ctx, const void* in_dev, void* out_dev, int batch, double radius, double shift_x,
+                   double shift_y, void* stream);
+/* measures.py:7-38 (eta, mean_x, mean_y, mean_x2, mean_xy, mean_y2), simulations/beam.py:26-33 (mean_x2_r)
+ * and simulations/pdt.py:21-26 + measures.py:7-8 (eta behind each aperture) in one sweep.
+ * pupils_dev: [npupil][3] (or [batch][npupil][3] when pupils_per_field) float32 {radius^2, shift_x, shift_y};
+ * out_dev: [batch][out_stride] float64, PA_MEASURE_HEAD values then one eta per aperture. */
+PA_API int pa_measure(pa_ctx* ctx, const void* field_dev, int batch, const float* pupils_dev, int npupil,
+               int pupils_per_field, double* out_dev, int out_stride, void* stream);
+/* simulations/pdt.py:30-31: numpy.histogram(values, bins, range) semantics; edges_dev has nbins+1 doubles */
+PA_API int pa_histogram(pa_ctx* ctx, const double* values_dev, size_t stride, size_t count, const double* edges_dev,
+                 int nbins, unsigned long long* counts_dev, void* stream);
+
+/* grids.py:98-107 + phase_screens.py:98-103 drawn on the device with Philox4x32-10 keyed by
+ * (seed; realization, screen, ring): production mode, independent of the number of GPUs. */
+PA_API int pa_rng_spectrum(pa_ctx* ctx, unsigned long long seed, unsigned long long realization0, int batch,
+                    int screen0, int nscreens, int m, const float* ring_edges_dev, const float* ring_psd_dev,
+                    float* fx_dev, float* fy_dev, float* coef_dev, void* stream);
+
+/* ---- fused path -------------------------------------------------------------------------------------------
+ * pathes.py:61-75 PhaseScreensPath.generator drained by lossless_output (:53-59), started from
+ * GaussianSource.output and followed (through_output) by AbstractPath.output (:23-24). */
+typedef struct pa_path {
+    int n_screens;
+    const double* leg_lengths_host;   /* n_screens + 1 entries: leg in front of each screen, then the closing leg */
+    const double* screen_scale_host;  /* n_screens entries: amplitude factor applied together with screen i */
+    double final_scale;               /* amplitude factor after the closing leg */
+    double wvl, w0, F0;               /* source */
+    int m, m_split, degree;           /* screens, see pa_screen_ss */
+    double shift_x, shift_y;
+    int screen_method;
+    int from_field;                   /* 0: start from the Gaussian source (generated inside the first pass);
+                                         1: field_dev already holds the input field in natural order */
+} pa_path;
+
+/* fx/fy/coef: [n_screens][batch][m] (one contiguous slab per path position); field_dev: [batch][N][N] result,
+ * natural order */
+PA_API int pa_propagate(pa_ctx* ctx, const pa_path* path, void* field_dev, int batch, const float* fx_dev,
+                 const float* fy_dev, const float* coef_dev, void* stream);
+
+/* One Monte-Carlo batch end to end (simulations/simulation.py:89-114 for BeamResult + PDTResult measures):
+ * coefficients come either from host buffers (coef_host != NULL: fx_host, fy_host, coef_host
+ * [n_screens][batch][m], copied host->device inside the call) or from the device RNG (coef_host == NULL, seed /
+ * realization0 / ring tables used).  The per-realization table [batch][out_stride] is copied to out_host and
+ * the call returns after the stream has drained.  The field buffer is ctx workspace. */
+PA_API int pa_simulate_batch(pa_ctx* ctx, const pa_path* path, int batch, const float* fx_host, const float* fy_host,
+                      const float* coef_host, unsigned long long seed, unsigned long long realization0,
+                      const float* ring_edges_dev, const float* ring_psd_dev, const float* pupils_host,
+                      int npupil, double* out_host, int out_stride, void* stream);
+/* same, everything stays on the device and nothing synchronises (throughput loop); table_dev [batch][out_stride] */
+PA_API int pa_simulate_batch_device(pa_ctx* ctx, const pa_path* path, int batch, unsigned long long seed,
+                             unsigned long long realization0, const float* ring_edges_dev,
+                             const float* ring_psd_dev, const float* pupils_dev, int npupil, double* table_dev,
+                             int out_stride, void* stream);
+
+/* One pass of the split-step FFT pipeline on a field that is in row-spectrum form, for profiling and for the
+ * roofline measurement of bench.py: kind 0 = column pass (FFT_y, x H, IFFT_y) of a leg of `length`;
+ * kind 1 = fused row pass (IFFT_x, x exp(-2 pi i turns), FFT_x), turns_dev may be NULL. */
+PA_API int pa_fft_pass(pa_ctx* ctx, void* field_dev, int batch, int kind, const void* turns_dev, double length,
+                       double wvl, void* stream);
+
+/* number of kernel launches issued by this library since the counter was last reset (bench.py gpu_launches) */
+PA_API unsigned long long pa_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYATM_B200_H */

@@ -1,0 +1,205 @@
+"""Host-side glue between the reference-shaped objects and the native library: context lookup, the split of
+the ring sum into polynomial + contraction, path descriptors, and the batched Monte-Carlo driver."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import _native as nat
+from . import gpu
+
+SCREEN_METHODS = {"exact": nat.PA_SCREEN_EXACT, "tc": nat.PA_SCREEN_TC}
+MAX_DEGREE = 63
+
+
+def channel_context(channel) -> nat.Context:
+    gpu.require_gpu()
+    grid = channel.grid
+    n = grid.resolution[0]
+    if grid.resolution[0] != grid.resolution[1]:
+        raise ValueError("only square grids are supported (the reference's get_f_grid / ifft2 assume it too)")
+    return nat.context(n, grid.delta, grid.get_x(), grid.get_y(), gpu.precision())
+
+
+def grid_context(grid) -> nat.Context:
+    gpu.require_gpu()
+    return nat.context(grid.resolution[0], grid.delta, grid.get_x(), grid.get_y(), gpu.precision())
+
+
+def plan_low_rings(ring_edges, ring_psd, x_extent, y_extent, theta_cut, tol):
+    """Choose (m_split, degree): rings [0, m_split) have phase arguments <= theta_cut everywhere on the grid
+    and are summed as a Taylor polynomial of total degree `degree` whose truncation error is below `tol` rad.
+
+    ring_edges: outer radii (monotone); ring_psd: phase variances.  |c_m| is bounded by 6 sqrt(psd_m)
+    (Rayleigh tail 1.5e-8).  The bound on the argument of ring m over the grid is
+    2 pi f_m sqrt(x_extent^2 + y_extent^2)."""
+    edges = np.asarray(ring_edges, dtype=np.float64)
+    psd = np.asarray(ring_psd, dtype=np.float64)
+    if theta_cut is None or theta_cut <= 0 or np.any(np.diff(edges) < 0):
+        return 0, -1
+    tmax = 2 * np.pi * edges * math.hypot(x_extent, y_extent)
+    m_split = int(np.searchsorted(tmax, theta_cut, side="right"))
+    amp = 6 * np.sqrt(np.maximum(psd, 0))
+    while m_split > 0:
+        t = tmax[:m_split]
+        a = amp[:m_split]
+        for deg in range(1, MAX_DEGREE + 1):
+            # log of sum_m a_m t_m^(deg+1) / (deg+1)!
+            err = np.sum(a * np.exp((deg + 1) * np.log(np.maximum(t, 1e-300)) - math.lgamma(deg + 2)))
+            if err <= tol:
+                return m_split, deg
+        m_split -= max(1, m_split // 16)
+    return 0, -1
+
+
+class PathDescriptor:
+    """Owns the ctypes pa_path and the host arrays it points to."""
+
+    def __init__(self, legs, screen_scale, final_scale, wvl, w0, F0, m, m_split, degree, shift, method, from_field):
+        self.legs = np.ascontiguousarray(legs, dtype=np.float64)
+        self.scales = np.ascontiguousarray(screen_scale if len(screen_scale) else [1.0], dtype=np.float64)
+        n_screens = len(self.legs) - 1
+        self.c = nat.PaPath(
+            n_screens=n_screens,
+            leg_lengths_host=self.legs.ctypes.data_as(C.POINTER(C.c_double)),
+            screen_scale_host=self.scales.ctypes.data_as(C.POINTER(C.c_double)),
+            final_scale=float(final_scale), wvl=float(wvl), w0=float(w0), F0=float(F0), m=int(m), m_split=int(m_split),
+            degree=int(degree), shift_x=float(shift[0]), shift_y=float(shift[1]), screen_method=int(method),
+            from_field=int(bool(from_field)))
+
+    def ref(self):
+        return C.byref(self.c)
+
+
+def loss_amplitude(db):
+    return 10 ** (-db / 20) if db else 1.0
+
+
+def path_losses(path, legs):
+    """Amplitude factors exactly as the reference applies dB losses (pathes.py:19-24,71-73): after screen i the
+    share losses*leg_i/length -- a share of exactly 0 falls back to the FULL loss because of
+    `losses_db or self.losses_db` -- and nothing for the closing leg."""
+    scales = []
+    for i in range(len(legs) - 1):
+        share = path.losses_db * legs[i] / path.length
+        scales.append(loss_amplitude(share or path.losses_db))
+    return scales
+
+
+def screen_tolerance():
+    return 1e-7 if gpu.precision() == 0 else 1e-12
+
+
+# ---- batched Monte-Carlo driver -----------------------------------------------------------------------------
+def table_columns(pupils_fixed, pupils_tracked):
+    """Column of every record in the table returned by simulate_realizations."""
+    cols = {name: i for i, name in enumerate(nat.MEASURE_NAMES)}
+    k = len(nat.MEASURE_NAMES)
+    for r in pupils_fixed:
+        cols[("fixed", r)] = k
+        k += 1
+    for r in pupils_tracked:
+        cols[("tracked", r)] = k
+        k += 1
+    return cols
+
+
+def draw_spectra_numpy(path, count):
+    """`count` realizations x S screens drawn from numpy's global RNG in the reference's order (realization-major,
+    then screen; per screen random(1), random(M), normal(2,M)).  Returns fx, fy [count][S][M] float32 and
+    coef [count][S][M] complex64."""
+    screens = path.phase_screens
+    S, M = len(screens), screens[0].f_grid.points
+    fx = np.empty((count, S, M), dtype=np.float32)
+    fy = np.empty((count, S, M), dtype=np.float32)
+    cf = np.empty((count, S, M), dtype=np.complex64)
+    for r in range(count):
+        for s, ps in enumerate(screens):
+            ps.cache_clear()
+            sp = ps._get_spectrum(use_cached_spectrum=False)
+            fx[r, s] = ps.f_grid.get_x(sp.rho, sp.theta)
+            fy[r, s] = ps.f_grid.get_y(sp.rho, sp.theta)
+            cf[r, s] = sp.value
+    return fx, fy, cf
+
+
+def _buffers(ctx, batch):
+    torch = nat.torch_mod()
+    buf = getattr(ctx, "_mc_buffers", None)
+    if buf is None or buf["field"].shape[0] < batch:
+        buf = {"field": ctx.empty_field(batch),
+               "table": torch.empty((batch, nat.MEASURE_HEAD + nat.MAX_PUPILS), dtype=torch.float64, device=ctx.tdevice),
+               "table2": torch.empty((batch, nat.MEASURE_HEAD + nat.MAX_PUPILS), dtype=torch.float64, device=ctx.tdevice)}
+        ctx._mc_buffers = buf
+    return buf
+
+
+def ring_tables(ctx, screen):
+    """Device copies of the ring edges and ring powers of a screen (inputs of the device RNG)."""
+    torch = nat.torch_mod()
+    key = id(screen.f_grid), screen._get_psd().ctypes.data
+    cache = getattr(ctx, "_ring_tables", {})
+    if key not in cache:
+        cache[key] = (torch.as_tensor(np.ascontiguousarray(screen.f_grid.base, dtype=np.float32), device=ctx.tdevice),
+                      torch.as_tensor(np.ascontiguousarray(screen._get_psd(), dtype=np.float32), device=ctx.tdevice))
+        ctx._ring_tables = cache
+    return cache[key]
+
+
+def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_tracked):
+    """Propagate the realizations with global indices `mine` (a contiguous block of [first, first+count)) and
+    reduce them.  Returns a float64 table [len(mine)][len(table_columns(...))]."""
+    ctx = channel_context(channel)
+    torch = nat.torch_mod()
+    path = channel.path
+    path.init_phase_screens()
+    S, M = len(path.phase_screens), path.phase_screens[0].f_grid.points
+    if len(pupils_fixed) > nat.MAX_PUPILS or len(pupils_tracked) > nat.MAX_PUPILS:
+        raise ValueError(f"at most {nat.MAX_PUPILS} fixed and {nat.MAX_PUPILS} tracked apertures per simulation")
+    cols = table_columns(pupils_fixed, pupils_tracked)
+    # numpy mode: every rank draws the whole batch so that the global RNG stream stays identical on all ranks
+    host = draw_spectra_numpy(path, count) if gpu.config["rng"] == "numpy" else None
+    B = len(mine)
+    if B == 0:
+        return np.zeros((0, len(cols)), dtype=np.float64)
+    dev = ctx.tdevice
+    buf = _buffers(ctx, B)
+    field, table, table2 = buf["field"], buf["table"], buf["table2"]
+    desc = path._descriptor((0, 0), through_output=False, from_field=False)
+    stream = nat.stream_ptr()
+    if host is not None:
+        sel = slice(int(mine[0] - first), int(mine[0] - first) + B)
+        fx_d = torch.as_tensor(np.ascontiguousarray(host[0][sel].transpose(1, 0, 2)), device=dev)     # [S][B][M]
+        fy_d = torch.as_tensor(np.ascontiguousarray(host[1][sel].transpose(1, 0, 2)), device=dev)
+        cf_d = torch.as_tensor(np.ascontiguousarray(host[2][sel].transpose(1, 0, 2)).view(np.float32), device=dev)
+    else:
+        edges_d, psd_d = ring_tables(ctx, path.phase_screens[0])
+        fx_d = torch.empty((S, B, M), dtype=torch.float32, device=dev)
+        fy_d = torch.empty((S, B, M), dtype=torch.float32, device=dev)
+        cf_d = torch.empty((S, B, M, 2), dtype=torch.float32, device=dev)
+        nat.check(ctx.lib.pa_rng_spectrum(ctx.handle, int(gpu.config["seed"]), int(mine[0]), B, 0, S, M, nat.ptr(edges_d),
+                                          nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
+    nat.check(ctx.lib.pa_propagate(ctx.handle, desc.ref(), nat.ptr(field), B, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
+    stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+    tab = np.array([[np.float32(r**2), 0, 0] for r in pupils_fixed], dtype=np.float32).reshape(-1, 3)
+    tab_d = torch.as_tensor(tab, device=dev) if len(pupils_fixed) else None
+    nat.check(ctx.lib.pa_measure(ctx.handle, nat.ptr(field), B, nat.ptr(tab_d), len(pupils_fixed), 0, nat.ptr(table), stride, stream))
+    out = np.empty((B, len(cols)), dtype=np.float64)
+    t1 = table[:B].cpu().numpy()
+    nm = len(nat.MEASURE_NAMES)
+    out[:, :nm] = t1[:, :nm]
+    out[:, nm:nm + len(pupils_fixed)] = t1[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + len(pupils_fixed)]
+    if pupils_tracked:
+        # aperture re-centred on each realization's centroid: shift = (mean_x, mean_y) (simulations/pdt.py:62-66)
+        per = np.empty((B, len(pupils_tracked), 3), dtype=np.float32)
+        for j, r in enumerate(pupils_tracked):
+            per[:, j, 0] = np.float32(r**2)
+            per[:, j, 1] = t1[:, 1].astype(np.float32)
+            per[:, j, 2] = t1[:, 2].astype(np.float32)
+        per_d = torch.as_tensor(per, device=dev)
+        nat.check(ctx.lib.pa_measure(ctx.handle, nat.ptr(field), B, nat.ptr(per_d), len(pupils_tracked), 1, nat.ptr(table2), stride, stream))
+        t2 = table2[:B].cpu().numpy()
+        out[:, nm + len(pupils_fixed):] = t2[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + len(pupils_tracked)]
+    return out

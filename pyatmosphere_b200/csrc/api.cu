@@ -1,0 +1,602 @@
+// C ABI of libpyatm_b200.so (see include/pyatm_b200.h): context, tables, and the orchestration of the
+// split-step passes.  Host code only; kernels live in fft_n*.cu, screen*.cu, measure.cu, rng.cu.
+#include "../../include/pyatm_b200.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <atomic>
+#include <complex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft_core.cuh"
+#include "internal.h"
+#include "internal_measure.h"
+#include "internal_rng.h"
+#include "internal_screen.h"
+
+namespace pa {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::atomic<unsigned long long> g_launches{0};
+static inline void note(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+struct HTable {
+    double length, wvl;
+    void* dev;            // cplx<T>[n] permuted transfer-function factor
+    double alpha_re, alpha_im;   // e^{ikL} / n^2
+};
+
+}  // namespace pa
+
+using namespace pa;
+
+struct pa_ctx {
+    int device = 0, n = 0, prec = 0, e = 0;
+    double delta = 0.0;
+    bool axes_set = false;
+    std::vector<float> hx, hy;         // host copies of the axes
+    float* x = nullptr;                // device axes
+    float* y = nullptr;
+    void* tw = nullptr;                // twiddles
+    std::vector<int> perm;             // frequency index held at storage position p
+    std::vector<HTable> htabs;
+    // workspace (grown on demand, never shrunk)
+    void* turns = nullptr; size_t turns_bytes = 0;
+    double* P = nullptr; double* Q = nullptr; size_t pq_bytes = 0;
+    double* polyc = nullptr; size_t polyc_bytes = 0;
+    double* partials = nullptr; size_t partials_bytes = 0;
+    void* field = nullptr; size_t field_bytes = 0;
+    float* spec = nullptr; size_t spec_bytes = 0;        // fx | fy | coef staging for pa_simulate_batch
+    float* pupils = nullptr; size_t pupils_bytes = 0;
+    double* table = nullptr; size_t table_bytes = 0;
+    size_t csize() const { return prec == 0 ? 8 : 16; }
+    size_t rsize() const { return prec == 0 ? 4 : 8; }
+};
+
+static int grow(void** p, size_t* have, size_t need) {
+    if (*have >= need) return PA_OK;
+    if (*p) PA_CUDA(cudaFree(*p));
+    *p = nullptr;
+    *have = 0;
+    PA_CUDA(cudaMalloc(p, need));
+    *have = need;
+    return PA_OK;
+}
+
+static int check_launch(int rc, const char* what) {
+    if (rc == 0) return PA_OK;
+    if (rc == -1) {
+        set_error("%s: unsupported grid size", what);
+        return PA_ERR_ARG;
+    }
+    set_error("%s: %s", what, cudaGetErrorString((cudaError_t)rc));
+    return PA_ERR_CUDA;
+}
+
+// ---- tables -------------------------------------------------------------------------------------------------
+template <typename T> static int build_twiddles(pa_ctx* c) {
+    const int n = c->n, e = c->e, L = plan_len(n, e);
+    const int total = plan_tw_size(n, e);
+    std::vector<cplx<T>> tw((size_t)(total > 0 ? total : 1));
+    for (int s = 0; s + 1 < L; ++s) {
+        const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s), nb = n / R, off = plan_tw_off(n, e, s);
+        for (int j = 1; j < R; ++j)
+            for (int b = 0; b < nb; ++b) {
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j * (long double)(b % sigma) /
+                                        (long double)(sigma * R);
+                tw[(size_t)off + (size_t)(j - 1) * nb + b] = mkc<T>((T)cosl(ang), (T)sinl(ang));
+            }
+    }
+    PA_CUDA(cudaMalloc(&c->tw, tw.size() * sizeof(cplx<T>)));
+    PA_CUDA(cudaMemcpy(c->tw, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    return PA_OK;
+}
+
+static void build_perm(pa_ctx* c) {
+    const int n = c->n, e = c->e, L = plan_len(n, e);
+    c->perm.resize(n);
+    for (int p = 0; p < n; ++p) {
+        int k = 0, mult = 1;
+        for (int s = 0; s < L; ++s) {
+            const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s);
+            k += ((p / sigma) % R) * mult;
+            mult *= R;
+        }
+        c->perm[p] = k;
+    }
+}
+
+// Transfer function of one leg, separable and in permuted order:
+//   H[ky][kx] = e^{ikL} h[ky] h[kx],  h[q] = exp(-i (pi L)(2 pi / k) f_q^2),  f_q = fl32(q~) * (1/(N delta))
+// evaluated with the reference's operation order (theory/vacuum.py:7, grids.py:63-69,82-85).
+static int get_htable(pa_ctx* c, double length, double wvl, const HTable** out) {
+    for (const auto& h : c->htabs)
+        if (h.length == length && h.wvl == wvl) {
+            *out = &h;
+            return PA_OK;
+        }
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called before propagating");
+    const int n = c->n;
+    const double k = 2 * M_PI / wvl;
+    const double df = 1 / ((double)n * c->delta);
+    const double coef = (M_PI * length) * (2 * M_PI / k);
+    HTable h;
+    h.length = length;
+    h.wvl = wvl;
+    h.dev = nullptr;
+    const double ang = k * length;
+    const double inv_n2 = 1.0 / ((double)n * (double)n);
+    h.alpha_re = cos(ang) * inv_n2;
+    h.alpha_im = sin(ang) * inv_n2;
+    std::vector<double> re(n), im(n);
+    for (int p = 0; p < n; ++p) {
+        const int q = c->perm[p];
+        const int qs = q < n / 2 ? q : q - n;
+        const double f = (double)(float)qs * df;
+        const double ph = -(coef * (f * f));
+        re[p] = cos(ph);
+        im[p] = sin(ph);
+    }
+    PA_CUDA(cudaMalloc(&h.dev, (size_t)n * c->csize()));
+    if (c->prec == 0) {
+        std::vector<float2> t(n);
+        for (int p = 0; p < n; ++p) t[p] = make_float2((float)re[p], (float)im[p]);
+        PA_CUDA(cudaMemcpy(h.dev, t.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double2> t(n);
+        for (int p = 0; p < n; ++p) t[p] = make_double2(re[p], im[p]);
+        PA_CUDA(cudaMemcpy(h.dev, t.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    c->htabs.push_back(h);
+    *out = &c->htabs.back();
+    return PA_OK;
+}
+
+// ---- pass helpers -----------------------------------------------------------------------------------------
+static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, bool src, const void* turns, double scale,
+                double amp, double aw, double ac, cudaStream_t st) {
+    RowLaunch r;
+    r.field = field;
+    r.tw = c->tw;
+    r.turns = turns;
+    r.scale = scale;
+    r.rows_total = batch * c->n;
+    r.in_perm = in_perm;
+    r.out_perm = out_perm;
+    r.src = src;
+    r.x = c->x;
+    r.y = c->y;
+    r.amp = amp;
+    r.aw = aw;
+    r.ac = ac;
+    note(1);
+    return check_launch(launch_rows(c->prec, c->n, r, st), "row pass");
+}
+static int cols(pa_ctx* c, void* field, int batch, double length, double wvl, cudaStream_t st) {
+    const HTable* h = nullptr;
+    int rc = get_htable(c, length, wvl, &h);
+    if (rc) return rc;
+    ColLaunch cl;
+    cl.field = field;
+    cl.tw = c->tw;
+    cl.hp = h->dev;
+    cl.alpha_re = h->alpha_re;
+    cl.alpha_im = h->alpha_im;
+    cl.batch = batch;
+    note(1);
+    return check_launch(launch_cols(c->prec, c->n, cl, st), "column pass");
+}
+
+static void source_params(double w0, double wvl, double F0, double* amp, double* aw, double* ac) {
+    *amp = sqrt(2 / M_PI) / w0;
+    *aw = 1 / (w0 * w0);
+    *ac = isinf(F0) ? 0.0 : 2 * M_PI / wvl / 2 / F0;
+}
+
+static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coef, int m, int m_split, int degree,
+                   double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method,
+                   cudaStream_t st) {
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called before generating screens");
+    PA_REQUIRE(m > 0 && m_split >= 0 && m_split <= m, "bad m / m_split (%d, %d)", m, m_split);
+    PA_REQUIRE(degree >= -1 && degree <= kMaxPolyDegree, "polynomial degree %d outside [-1, %d]", degree, kMaxPolyDegree);
+    PA_REQUIRE(m_split == 0 || degree >= 0, "m_split > 0 needs degree >= 0");
+    PA_REQUIRE(method == PA_SCREEN_EXACT, "screen method %d not available in this build", method);
+    const int n = c->n;
+    const int k2 = 2 * (m - m_split);
+    PA_REQUIRE(c->pq_bytes >= (size_t)nscreens * (k2 > 0 ? k2 : 1) * n * sizeof(double), "screen workspace not reserved");
+    ScreenLaunch a;
+    a.n = n;
+    a.m = m;
+    a.m_split = m_split;
+    a.degree = m_split > 0 ? degree : -1;
+    a.nscreens = nscreens;
+    a.x = c->x;
+    a.y = c->y;
+    a.shift_x = (float)shift_x;
+    a.shift_y = (float)shift_y;
+    double x0 = 0, y0 = 0;
+    for (int i = 0; i < n; ++i) {
+        x0 = fmax(x0, fabs((double)(c->hx[i] + a.shift_x)));
+        y0 = fmax(y0, fabs((double)(c->hy[i] + a.shift_y)));
+    }
+    if (x0 == 0) x0 = 1;
+    if (y0 == 0) y0 = 1;
+    a.x0 = x0;
+    a.y0 = y0;
+    a.inv_x0 = 1 / x0;
+    a.inv_y0 = 1 / y0;
+    a.fx = fx;
+    a.fy = fy;
+    a.coef = (const float2*)coef;
+    a.P = c->P;
+    a.Q = c->Q;
+    a.polyc = c->polyc;
+    a.turns = turns;
+    a.turns_f64 = c->prec == 1;
+    a.phi = phi;
+    a.phi_f64 = phi_f64;
+    note(3);
+    return check_launch(launch_screen_exact(a, st), "screen synthesis");
+}
+
+static int ensure_screen_ws(pa_ctx* c, int nscreens, int m, int m_split, int degree) {
+    const int k2 = 2 * (m - m_split);
+    const size_t need = (size_t)nscreens * (k2 > 0 ? k2 : 1) * c->n * sizeof(double);
+    if (c->pq_bytes < need) {
+        if (c->P) PA_CUDA(cudaFree(c->P));
+        if (c->Q) PA_CUDA(cudaFree(c->Q));
+        c->P = c->Q = nullptr;
+        c->pq_bytes = 0;
+        PA_CUDA(cudaMalloc((void**)&c->P, need));
+        PA_CUDA(cudaMalloc((void**)&c->Q, need));
+        c->pq_bytes = need;
+    }
+    const size_t pneed = (size_t)nscreens * (degree + 2) * (degree + 2) * sizeof(double);
+    return grow((void**)&c->polyc, &c->polyc_bytes, pneed);
+}
+
+// ---- exported functions ----------------------------------------------------------------------------------
+extern "C" {
+
+int pa_version(void) { return PA_VERSION; }
+const char* pa_last_error(void) { return last_error(); }
+int pa_device_count(int* count) {
+    PA_CUDA(cudaGetDeviceCount(count));
+    return PA_OK;
+}
+unsigned long long pa_launch_count(int reset) {
+    return reset ? g_launches.exchange(0) : g_launches.load();
+}
+
+int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
+    PA_REQUIRE(out != nullptr, "null ctx pointer");
+    PA_REQUIRE(precision == PA_C64 || precision == PA_C128, "precision must be PA_C64 or PA_C128");
+    PA_REQUIRE(fft_size_supported(precision, n), "grid size %d unsupported: power of two in [64, 8192] required", n);
+    PA_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PA_CUDA(cudaGetDeviceProperties(&prop, device));
+    PA_REQUIRE(prop.major == 10, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    pa_ctx* c = new pa_ctx();
+    c->device = device;
+    c->n = n;
+    c->prec = precision;
+    c->e = elems_per_thread(precision);
+    build_perm(c);
+    int rc = precision == 0 ? build_twiddles<float>(c) : build_twiddles<double>(c);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    rc = screen_init_constants();
+    if (rc) {
+        set_error("constant upload failed: %s", cudaGetErrorString((cudaError_t)rc));
+        delete c;
+        return PA_ERR_CUDA;
+    }
+    c->htabs.reserve(256);
+    *out = c;
+    return PA_OK;
+}
+
+int pa_ctx_destroy(pa_ctx* c) {
+    if (!c) return PA_OK;
+    cudaSetDevice(c->device);
+    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (auto& h : c->htabs)
+        if (h.dev) cudaFree(h.dev);
+    delete c;
+    return PA_OK;
+}
+
+int pa_ctx_set_axes(pa_ctx* c, const float* x_host, const float* y_host, double delta) {
+    PA_REQUIRE(c && x_host && y_host && delta > 0, "bad arguments to pa_ctx_set_axes");
+    PA_CUDA(cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->n * sizeof(float);
+    if (!c->x) PA_CUDA(cudaMalloc((void**)&c->x, bytes));
+    if (!c->y) PA_CUDA(cudaMalloc((void**)&c->y, bytes));
+    PA_CUDA(cudaMemcpy(c->x, x_host, bytes, cudaMemcpyHostToDevice));
+    PA_CUDA(cudaMemcpy(c->y, y_host, bytes, cudaMemcpyHostToDevice));
+    c->hx.assign(x_host, x_host + c->n);
+    c->hy.assign(y_host, y_host + c->n);
+    if (c->delta != delta) {
+        for (auto& h : c->htabs)
+            if (h.dev) cudaFree(h.dev);
+        c->htabs.clear();
+    }
+    c->delta = delta;
+    c->axes_set = true;
+    return PA_OK;
+}
+
+int pa_ctx_permutation(pa_ctx* c, int* perm_host) {
+    PA_REQUIRE(c && perm_host, "bad arguments");
+    memcpy(perm_host, c->perm.data(), (size_t)c->n * sizeof(int));
+    return PA_OK;
+}
+
+int pa_ctx_fft_geometry(pa_ctx* c, int* g) {
+    PA_REQUIRE(c && g, "bad arguments");
+    fft_geometry(c->prec, c->n, &g[0], &g[1], &g[2], &g[3], &g[4], &g[5]);
+    return PA_OK;
+}
+
+int pa_source_gaussian(pa_ctx* c, void* field, int batch, double w0, double wvl, double F0, void* stream) {
+    PA_REQUIRE(c && field && batch > 0 && w0 > 0 && wvl > 0, "bad arguments to pa_source_gaussian");
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called first");
+    double amp, aw, ac;
+    source_params(w0, wvl, F0, &amp, &aw, &ac);
+    return rows(c, field, batch, false, false, true, nullptr, 1.0, amp, aw, ac, (cudaStream_t)stream);
+}
+
+int pa_vacuum_leg(pa_ctx* c, void* field, int batch, double length, double wvl, void* stream) {
+    PA_REQUIRE(c && field && batch > 0 && wvl > 0, "bad arguments to pa_vacuum_leg");
+    if (!(length > 0)) return PA_OK;   // pathes.py:30,39-40
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = rows(c, field, batch, false, true, false, nullptr, 1.0, 0, 0, 0, st);
+    if (rc) return rc;
+    rc = cols(c, field, batch, length, wvl, st);
+    if (rc) return rc;
+    return rows(c, field, batch, true, false, false, nullptr, 1.0, 0, 0, 0, st);
+}
+
+int pa_screen_ss(pa_ctx* c, const float* fx, const float* fy, const float* coef, int m, int m_split, int degree,
+                 double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method, void* stream) {
+    PA_REQUIRE(c && fx && fy && coef && nscreens > 0, "bad arguments to pa_screen_ss");
+    PA_REQUIRE(turns || phi, "pa_screen_ss needs at least one output");
+    int rc = ensure_screen_ws(c, nscreens, m, m_split, degree);
+    if (rc) return rc;
+    return screens(c, fx, fy, coef, m, m_split, degree, shift_x, shift_y, nscreens, turns, phi, phi_f64, method, (cudaStream_t)stream);
+}
+
+int pa_apply_screen(pa_ctx* c, void* field, int batch, const void* turns, double scale, void* stream) {
+    PA_REQUIRE(c && field && batch > 0, "bad arguments to pa_apply_screen");
+    return rows(c, field, batch, false, false, false, turns, scale, 0, 0, 0, (cudaStream_t)stream);
+}
+
+int pa_phase_to_turns(pa_ctx* c, const void* phi, int phi_f64, void* turns, size_t count, void* stream) {
+    PA_REQUIRE(c && phi && turns, "bad arguments to pa_phase_to_turns");
+    note(1);
+    return check_launch(launch_phase_to_turns(phi, phi_f64, turns, c->prec == 1, count, (cudaStream_t)stream), "phase_to_turns");
+}
+
+int pa_intensity(pa_ctx* c, const void* field, void* out, int batch, void* stream) {
+    PA_REQUIRE(c && field && out && batch > 0, "bad arguments to pa_intensity");
+    note(1);
+    return check_launch(launch_intensity(c->prec, field, out, (size_t)batch * c->n * c->n, (cudaStream_t)stream), "intensity");
+}
+
+int pa_pupil_apply(pa_ctx* c, const void* in, void* out, int batch, double radius, double sx, double sy, void* stream) {
+    PA_REQUIRE(c && in && out && batch > 0, "bad arguments to pa_pupil_apply");
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called first");
+    note(1);
+    return check_launch(launch_pupil(c->prec, in, out, c->x, c->y, c->n, batch, (float)(radius * radius), (float)sx, (float)sy,
+                                     (cudaStream_t)stream), "pupil");
+}
+
+int pa_measure(pa_ctx* c, const void* field, int batch, const float* pupils, int npupil, int per_field, double* out,
+               int out_stride, void* stream) {
+    PA_REQUIRE(c && field && out && batch > 0, "bad arguments to pa_measure");
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called first");
+    PA_REQUIRE(npupil >= 0 && npupil <= kMaxPupils, "at most %d apertures per pa_measure call", kMaxPupils);
+    PA_REQUIRE(npupil == 0 || pupils, "pupil table missing");
+    PA_REQUIRE(out_stride >= kMeasureHead + npupil, "out_stride too small");
+    const int nparts = c->n / 8 < 148 ? c->n / 8 : 148;
+    int rc = grow((void**)&c->partials, &c->partials_bytes, (size_t)batch * nparts * (kRawMoments + kMaxPupils) * sizeof(double));
+    if (rc) return rc;
+    MeasureLaunch a;
+    a.field = field;
+    a.n = c->n;
+    a.batch = batch;
+    a.x = c->x;
+    a.y = c->y;
+    a.delta2 = c->delta * c->delta;
+    a.pupils = pupils;
+    a.npupil = npupil;
+    a.pupils_per_field = per_field;
+    a.partials = c->partials;
+    a.nparts = nparts;
+    a.out = out;
+    a.out_stride = out_stride;
+    note(2);
+    return check_launch(launch_measure(c->prec, a, (cudaStream_t)stream), "measure");
+}
+
+int pa_histogram(pa_ctx* c, const double* values, size_t stride, size_t count, const double* edges, int nbins,
+                 unsigned long long* counts, void* stream) {
+    PA_REQUIRE(c && values && edges && counts && nbins > 0, "bad arguments to pa_histogram");
+    if (count == 0) return PA_OK;
+    note(1);
+    return check_launch(launch_histogram(values, stride, count, edges, nbins, counts, (cudaStream_t)stream), "histogram");
+}
+
+int pa_rng_spectrum(pa_ctx* c, unsigned long long seed, unsigned long long realization0, int batch, int screen0, int nscreens,
+                    int m, const float* edges, const float* psd, float* fx, float* fy, float* coef, void* stream) {
+    PA_REQUIRE(c && edges && psd && fx && fy && coef && batch > 0 && nscreens > 0 && m > 0, "bad arguments to pa_rng_spectrum");
+    RngLaunch a;
+    a.seed = seed;
+    a.realization0 = realization0;
+    a.realization_stride = 1;
+    a.screen0 = screen0;
+    a.nscreens = nscreens;
+    a.batch = batch;
+    a.m = m;
+    a.base = edges;
+    a.psd = psd;
+    a.fx = fx;
+    a.fy = fy;
+    a.coef = (float2*)coef;
+    a.rho = nullptr;
+    a.theta = nullptr;
+    note(1);
+    return check_launch(launch_rng_spectrum(a, (cudaStream_t)stream), "rng_spectrum");
+}
+
+int pa_fft_pass(pa_ctx* c, void* field, int batch, int kind, const void* turns, double length, double wvl, void* stream) {
+    PA_REQUIRE(c && field && batch > 0 && (kind == 0 || kind == 1), "bad arguments to pa_fft_pass");
+    if (kind == 0) return cols(c, field, batch, length, wvl, (cudaStream_t)stream);
+    return rows(c, field, batch, true, true, false, turns, 1.0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+// Token stream of one realization: SRC, then for every screen [leg] screen, then [closing leg].  A leg is
+// FFT_x | columns | IFFT_x; all row-level tokens between two column passes are fused into one k_rows launch.
+int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const float* fx, const float* fy, const float* coef,
+                 void* stream) {
+    PA_REQUIRE(c && p && field && batch > 0, "bad arguments to pa_propagate");
+    PA_REQUIRE(p->n_screens >= 0 && p->leg_lengths_host, "bad path description");
+    PA_REQUIRE(p->n_screens == 0 || (fx && fy && coef && p->screen_scale_host), "screen coefficients missing");
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called first");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = p->n_screens, n = c->n;
+    int rc;
+    if (S > 0) {
+        rc = ensure_screen_ws(c, batch, p->m, p->m_split, p->degree);
+        if (rc) return rc;
+        rc = grow(&c->turns, &c->turns_bytes, (size_t)batch * n * n * c->rsize());
+        if (rc) return rc;
+    }
+    double amp, aw, ac;
+    source_params(p->w0, p->wvl, p->F0, &amp, &aw, &ac);
+
+    // state of the field between launches
+    bool have_field = p->from_field != 0;   // false: the source has not been materialised yet
+    bool perm = false;         // true: field is in row-spectrum form awaiting IFFT_x
+    // one fused row launch: [SRC | IFFT_x]? [screen]? [FFT_x]?
+    auto row_launch = [&](bool want_perm_out, const void* turns, double scale) -> int {
+        const bool src = !have_field;
+        int r = rows(c, field, batch, perm, want_perm_out, src, turns, scale, amp, aw, ac, st);
+        have_field = true;
+        perm = want_perm_out;
+        return r;
+    };
+    auto gen_screen = [&](int i) -> int {   // coefficient arrays are [S][batch][m]: one contiguous slab per path position
+        const size_t o = (size_t)i * batch * p->m;
+        return screens(c, fx + o, fy + o, coef + 2 * o, p->m, p->m_split, p->degree, p->shift_x, p->shift_y, batch, c->turns,
+                       nullptr, 0, p->screen_method, st);
+    };
+
+    for (int i = 0; i < S; ++i) {
+        const double L = p->leg_lengths_host[i];
+        if (L > 0) {
+            if (!perm) {                       // leading FFT_x of this leg was not fused into a previous launch
+                rc = row_launch(true, nullptr, 1.0);
+                if (rc) return rc;
+            }
+            rc = cols(c, field, batch, L, p->wvl, st);
+            if (rc) return rc;
+        }
+        rc = gen_screen(i);
+        if (rc) return rc;
+        const double Lnext = p->leg_lengths_host[i + 1];
+        double scale = p->screen_scale_host[i];
+        const bool fuse_next = Lnext > 0;
+        if (i == S - 1 && !fuse_next) scale *= p->final_scale;
+        rc = row_launch(fuse_next, c->turns, scale);
+        if (rc) return rc;
+    }
+    const double Llast = p->leg_lengths_host[S];
+    if (Llast > 0) {
+        if (!perm) {
+            rc = row_launch(true, nullptr, 1.0);
+            if (rc) return rc;
+        }
+        rc = cols(c, field, batch, Llast, p->wvl, st);
+        if (rc) return rc;
+        rc = row_launch(false, nullptr, p->final_scale);
+        if (rc) return rc;
+    } else if (S == 0) {
+        rc = row_launch(false, nullptr, p->final_scale);
+        if (rc) return rc;
+    }
+    return PA_OK;
+}
+
+static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host,
+                           const float* coef_host, unsigned long long seed, unsigned long long realization0,
+                           const float* edges, const float* psd, const float* pupils_dev, int npupil, double* table_dev,
+                           int out_stride, cudaStream_t st) {
+    const int S = p->n_screens, m = p->m, n = c->n;
+    int rc = grow(&c->field, &c->field_bytes, (size_t)batch * n * n * c->csize());
+    if (rc) return rc;
+    const size_t cnt = (size_t)batch * (S > 0 ? S : 1) * m;
+    rc = grow((void**)&c->spec, &c->spec_bytes, cnt * 4 * sizeof(float));
+    if (rc) return rc;
+    float* fx = c->spec;
+    float* fy = c->spec + cnt;
+    float* coef = c->spec + 2 * cnt;
+    if (S > 0) {
+        if (coef_host) {
+            PA_CUDA(cudaMemcpyAsync(fx, fx_host, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(fy, fy_host, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(coef, coef_host, cnt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else {
+            rc = pa_rng_spectrum(c, seed, realization0, batch, 0, S, m, edges, psd, fx, fy, coef, st);
+            if (rc) return rc;
+        }
+    }
+    rc = pa_propagate(c, p, c->field, batch, fx, fy, coef, st);
+    if (rc) return rc;
+    return pa_measure(c, c->field, batch, pupils_dev, npupil, 0, table_dev, out_stride, st);
+}
+
+int pa_simulate_batch(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,
+                      unsigned long long seed, unsigned long long realization0, const float* edges, const float* psd,
+                      const float* pupils_host, int npupil, double* out_host, int out_stride, void* stream) {
+    PA_REQUIRE(c && p && out_host && batch > 0, "bad arguments to pa_simulate_batch");
+    PA_REQUIRE(coef_host || (edges && psd) || p->n_screens == 0, "either host coefficients or ring tables are required");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = grow((void**)&c->table, &c->table_bytes, (size_t)batch * out_stride * sizeof(double));
+    if (rc) return rc;
+    rc = grow((void**)&c->pupils, &c->pupils_bytes, (size_t)(npupil > 0 ? npupil : 1) * 3 * sizeof(float));
+    if (rc) return rc;
+    if (npupil > 0) PA_CUDA(cudaMemcpyAsync(c->pupils, pupils_host, (size_t)npupil * 3 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = simulate_common(c, p, batch, fx_host, fy_host, coef_host, seed, realization0, edges, psd, c->pupils, npupil, c->table,
+                         out_stride, st);
+    if (rc) return rc;
+    PA_CUDA(cudaMemcpyAsync(out_host, c->table, (size_t)batch * out_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    PA_CUDA(cudaStreamSynchronize(st));
+    return PA_OK;
+}
+
+int pa_simulate_batch_device(pa_ctx* c, const pa_path* p, int batch, unsigned long long seed, unsigned long long realization0,
+                             const float* edges, const float* psd, const float* pupils_dev, int npupil, double* table_dev,
+                             int out_stride, void* stream) {
+    PA_REQUIRE(c && p && table_dev && batch > 0, "bad arguments to pa_simulate_batch_device");
+    PA_REQUIRE((edges && psd) || p->n_screens == 0, "ring tables are required");
+    return simulate_common(c, p, batch, nullptr, nullptr, nullptr, seed, realization0, edges, psd, pupils_dev, npupil, table_dev,
+                           out_stride, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,72 @@
+// Shared helpers for the pyatmosphere_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace pa {
+
+// ---- error plumbing (status codes cross the C ABI, text stays here) --------------------------------
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define PA_OK 0
+#define PA_ERR_ARG 1
+#define PA_ERR_CUDA 2
+#define PA_ERR_STATE 3
+
+#define PA_CUDA(call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            pa::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+            return PA_ERR_CUDA;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+#define PA_REQUIRE(cond, ...)                                                                       \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            pa::set_error(__VA_ARGS__);                                                             \
+            return PA_ERR_ARG;                                                                      \
+        }                                                                                           \
+    } while (0)
+
+// ---- complex arithmetic on float2 / double2 ---------------------------------------------------------
+template <typename T> struct cx2;
+template <> struct cx2<float> { using type = float2; };
+template <> struct cx2<double> { using type = double2; };
+template <typename T> using cplx = typename cx2<T>::type;
+
+template <typename T> __host__ __device__ __forceinline__ cplx<T> mkc(T a, T b) {
+    cplx<T> r;
+    r.x = a;
+    r.y = b;
+    return r;
+}
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+// a * b
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r;
+    r.x = a.x * b.x - a.y * b.y;
+    r.y = a.x * b.y + a.y * b.x;
+    return r;
+}
+// a * conj(b)
+template <typename C> __device__ __forceinline__ C cmulc(C a, C b) {
+    C r;
+    r.x = a.x * b.x + a.y * b.y;
+    r.y = a.y * b.x - a.x * b.y;
+    return r;
+}
+// a * (-i)
+template <typename C> __device__ __forceinline__ C cmul_mi(C a) { C r; r.x = a.y; r.y = -a.x; return r; }
+// a * (+i)
+template <typename C> __device__ __forceinline__ C cmul_pi(C a) { C r; r.x = -a.y; r.y = a.x; return r; }
+template <typename C> __device__ __forceinline__ C cswap(C a) { C r; r.x = a.y; r.y = a.x; return r; }
+
+__host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+
+}  // namespace pa

@@ -1,0 +1,47 @@
+// Internal (non-ABI) interfaces between the translation units of libpyatm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pa {
+
+// elements per thread of the register FFT, per precision (0 = complex64, 1 = complex128)
+constexpr int kE32 = 16;
+constexpr int kE64 = 8;
+inline int elems_per_thread(int prec) { return prec == 0 ? kE32 : kE64; }
+
+struct RowLaunch {
+    void* field;          // cplx<T>* [rows_total][n]
+    const void* tw;       // cplx<T>* twiddles
+    const void* turns;    // T* or null
+    double scale;
+    int rows_total;
+    bool in_perm, out_perm, src;
+    const float* x;
+    const float* y;
+    double amp, aw, ac;
+};
+struct ColLaunch {
+    void* field;          // cplx<T>* [batch][n][n]
+    const void* tw;
+    const void* hp;       // cplx<T>* permuted transfer-function factor
+    double alpha_re, alpha_im;
+    int batch;
+};
+
+// implemented once per grid size in fft_n<N>.cu; return cudaError_t as int, or -1 for an unsupported size
+int launch_rows(int prec, int n, const RowLaunch& a, cudaStream_t st);
+int launch_cols(int prec, int n, const ColLaunch& a, cudaStream_t st);
+bool fft_size_supported(int prec, int n);
+// number of CTAs / threads / smem of the two passes (reported through pa_fft_geometry for the roofline notes)
+void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_smem, int* cols_threads, int* cols_tc, int* cols_smem);
+
+#define PA_FFT_SIZES(X) X(64) X(128) X(256) X(512) X(1024) X(2048) X(4096) X(8192)
+#define PA_DECL(N)                                                                   \
+    int launch_rows_##N(int prec, const RowLaunch& a, cudaStream_t st);              \
+    int launch_cols_##N(int prec, const ColLaunch& a, cudaStream_t st);              \
+    void fft_geometry_##N(int prec, int* g);
+PA_FFT_SIZES(PA_DECL)
+#undef PA_DECL
+
+}  // namespace pa

@@ -1,0 +1,34 @@
+// Internal launch descriptor of the phase-screen kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pa {
+
+constexpr int kMaxPolyDegree = 63;
+
+struct ScreenLaunch {
+    int n;              // grid size
+    int m;              // harmonics per screen
+    int m_split;        // harmonics [0, m_split) go to the polynomial, [m_split, m) to the contraction
+    int degree;         // total degree of the polynomial, -1 = none
+    int nscreens;       // screens in this launch (batch)
+    const float* x;     // [n] float32 axes as the reference builds them (grids.py:63-69)
+    const float* y;
+    float shift_x, shift_y;
+    double x0, y0, inv_x0, inv_y0;   // normalisation of the polynomial variables: xh = xs / x0
+    const float* fx;    // [nscreens][m]
+    const float* fy;    // [nscreens][m]
+    const float2* coef; // [nscreens][m]
+    double* P;          // workspace [nscreens][2 (m - m_split)][n]
+    double* Q;          // workspace [nscreens][2 (m - m_split)][n]
+    double* polyc;      // workspace [nscreens][(degree+1)^2]
+    void* turns;        // out [nscreens][n][n] float or double, may be null
+    int turns_f64;
+    void* phi;          // out, optional full phase [nscreens][n][n] float or double
+    int phi_f64;
+};
+
+int screen_init_constants();
+int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st);
+
+}  // namespace pa

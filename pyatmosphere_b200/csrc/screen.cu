@@ -1,0 +1,228 @@
+// Sparse-spectrum phase-screen synthesis (replaces SSPhaseScreen.generate_phase_screen,
+// /root/reference/pyatmosphere/phase_screens.py:108-136, contraction at :125-126).
+//
+//   phi[i][j] = Re sum_m c_m exp(2 pi i ys_i fy_m) exp(2 pi i fx_m xs_j),  xs = fl32(x + sx), ys = fl32(y + sy)
+//
+// Rings are ordered by radius (RandLogPolarGrid annuli are nested), so the sum is split at m_split:
+//   * m <  m_split ("low" rings: huge |c_m|, arguments <= theta_cut over the whole grid): the sum of harmonics
+//     is a bivariate polynomial  sum_{p+q<=D} T_pq xh^p yh^q  (Taylor series of exp), evaluated in float64.
+//   * m >= m_split ("high" rings): real contraction  phi_hi = P^T Q  with K2 = 2 (M - m_split) rows,
+//       P[2k][i] = Re(c a_i), P[2k+1][i] = -Im(c a_i), Q[2k][j] = cos(2 pi fx xs_j), Q[2k+1][j] = sin(...).
+// This file holds the float64 CUDA-core contraction (exact path, used for complex128 runs and as the on-device
+// check of the tensor-core path in screen_tc.cu).  The result is written as "turns" = frac(phi / 2 pi) in
+// [-0.5, 0.5] (what the row pass consumes) and, optionally, as the full phase.
+#include "common.cuh"
+#include "internal_screen.h"
+
+namespace pa {
+
+__constant__ double c_invfact[kMaxPolyDegree + 2];
+
+int screen_init_constants() {
+    double f[kMaxPolyDegree + 2];
+    double acc = 1.0;
+    f[0] = 1.0;
+    for (int i = 1; i < kMaxPolyDegree + 2; ++i) {
+        acc *= (double)i;
+        f[i] = 1.0 / acc;
+    }
+    return (int)cudaMemcpyToSymbol(c_invfact, f, sizeof(f));
+}
+
+// ---- factor rows for the high rings, float64 ------------------------------------------------------------
+// grid: (ceil(n/256), m - m_split, nscreens)
+__global__ void k_screen_factors64(ScreenLaunch a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    const int s = blockIdx.z;
+    if (i >= a.n) return;
+    const int m = a.m_split + k;
+    const float fx = a.fx[(size_t)s * a.m + m];
+    const float fy = a.fy[(size_t)s * a.m + m];
+    const float2 c = a.coef[(size_t)s * a.m + m];
+    const int k2 = 2 * (a.m - a.m_split);
+    double* P = a.P + ((size_t)s * k2 + 2 * k) * a.n;
+    double* Q = a.Q + ((size_t)s * k2 + 2 * k) * a.n;
+    const double ys = (double)__fadd_rn(a.y[i], a.shift_y);
+    const double xs = (double)__fadd_rn(a.x[i], a.shift_x);
+    double sa, ca, sb, cb;
+    sincospi(2.0 * (ys * (double)fy), &sa, &ca);
+    sincospi(2.0 * (xs * (double)fx), &sb, &cb);
+    P[i] = (double)c.x * ca - (double)c.y * sa;
+    P[a.n + i] = -((double)c.x * sa + (double)c.y * ca);
+    Q[i] = cb;
+    Q[a.n + i] = sb;
+}
+
+// ---- polynomial coefficients of the low rings -----------------------------------------------------------
+// T^_pq = Re( i^(p+q) sum_{m<m_split} c_m (2 pi fx_m X0)^p (2 pi fy_m Y0)^q ) / (p! q!)
+// grid: ((D+1)^2, nscreens), block 128.  Entries with p+q > D are written as 0.
+__global__ void k_screen_poly_coef(ScreenLaunch a) {
+    const int D = a.degree;
+    const int p = blockIdx.x / (D + 1);
+    const int q = blockIdx.x % (D + 1);
+    const int s = blockIdx.y;
+    double* out = a.polyc + (size_t)s * (D + 1) * (D + 1) + blockIdx.x;
+    if (p + q > D) {
+        if (threadIdx.x == 0) *out = 0.0;
+        return;
+    }
+    double sr = 0.0, si = 0.0;
+    for (int m = threadIdx.x; m < a.m_split; m += blockDim.x) {
+        const double fa = 6.283185307179586476925287 * (double)a.fx[(size_t)s * a.m + m] * a.x0;
+        const double fb = 6.283185307179586476925287 * (double)a.fy[(size_t)s * a.m + m] * a.y0;
+        double w = 1.0;
+        for (int u = 0; u < p; ++u) w *= fa;
+        for (int u = 0; u < q; ++u) w *= fb;
+        const float2 c = a.coef[(size_t)s * a.m + m];
+        sr += (double)c.x * w;
+        si += (double)c.y * w;
+    }
+    __shared__ double red[2][4];
+    for (int o = 16; o > 0; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o);
+        si += __shfl_xor_sync(0xffffffffu, si, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[0][threadIdx.x >> 5] = sr;
+        red[1][threadIdx.x >> 5] = si;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        sr = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        si = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        double v;
+        switch ((p + q) & 3) {   // Re(i^k (sr + i si))
+            case 0: v = sr; break;
+            case 1: v = -si; break;
+            case 2: v = -sr; break;
+            default: v = si; break;
+        }
+        *out = v * c_invfact[p] * c_invfact[q];
+    }
+}
+
+// ---- float64 contraction + epilogue -----------------------------------------------------------------------
+// tile 64 (i) x 64 (j), 256 threads, 4x4 outputs per thread, K chunk 16.  grid: (n/64, n/64, nscreens)
+constexpr int kTS = 64;
+constexpr int kKC = 16;
+
+template <typename TOUT>
+__global__ void __launch_bounds__(256) k_screen_gemm64(ScreenLaunch a) {
+    extern __shared__ __align__(16) double smd[];
+    double* sP = smd;                    // [2][kKC][kTS]
+    double* sQ = smd + 2 * kKC * kTS;    // [2][kKC][kTS]
+    const int s = blockIdx.z;
+    const int i0 = blockIdx.y * kTS;
+    const int j0 = blockIdx.x * kTS;
+    const int tx = threadIdx.x % 16;     // j direction
+    const int ty = threadIdx.x / 16;     // i direction
+    const int k2 = 2 * (a.m - a.m_split);
+    const double* P = a.P + (size_t)s * k2 * a.n;
+    const double* Q = a.Q + (size_t)s * k2 * a.n;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int w = 0; w < 4; ++w) acc[u][w] = 0.0;
+
+    // each thread loads 4 doubles of P and 4 of Q per chunk: chunk has 16*64 = 1024 per matrix
+    const int lk = threadIdx.x / 16;           // 0..15
+    const int li = (threadIdx.x % 16) * 4;     // 0..60
+    auto load = [&](int buf, int kc) {
+        const int k = kc * kKC + lk;
+        double2 p0 = make_double2(0, 0), p1 = p0, q0 = p0, q1 = p0;
+        if (k < k2) {
+            const double2* pp = reinterpret_cast<const double2*>(P + (size_t)k * a.n + i0 + li);
+            const double2* qq = reinterpret_cast<const double2*>(Q + (size_t)k * a.n + j0 + li);
+            p0 = pp[0]; p1 = pp[1]; q0 = qq[0]; q1 = qq[1];
+        }
+        double2* dp = reinterpret_cast<double2*>(sP + ((size_t)buf * kKC + lk) * kTS + li);
+        double2* dq = reinterpret_cast<double2*>(sQ + ((size_t)buf * kKC + lk) * kTS + li);
+        dp[0] = p0; dp[1] = p1; dq[0] = q0; dq[1] = q1;
+    };
+    const int nchunk = (k2 + kKC - 1) / kKC;
+    if (nchunk > 0) load(0, 0);
+    __syncthreads();
+    for (int kc = 0; kc < nchunk; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < nchunk) load(buf ^ 1, kc + 1);
+#pragma unroll
+        for (int kk = 0; kk < kKC; ++kk) {
+            const double2* pr = reinterpret_cast<const double2*>(sP + ((size_t)buf * kKC + kk) * kTS + ty * 4);
+            const double2* qr = reinterpret_cast<const double2*>(sQ + ((size_t)buf * kKC + kk) * kTS + tx * 4);
+            const double2 pa = pr[0], pb = pr[1], qa = qr[0], qb = qr[1];
+            const double pv[4] = {pa.x, pa.y, pb.x, pb.y};
+            const double qv[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) acc[u][w] = fma(pv[u], qv[w], acc[u][w]);
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: low-ring polynomial + reduction to turns --------------------------------------------
+    const int D = a.degree;
+    double* sU = smd;      // [(D+1)][kTS] : U_p(yh_i) = sum_q T^_pq yh^q   (reuses the GEMM buffers)
+    if (D >= 0) {
+        const double* tc = a.polyc + (size_t)s * (D + 1) * (D + 1);
+        for (int e = threadIdx.x; e < (D + 1) * kTS; e += blockDim.x) {
+            const int p = e / kTS, ii = e % kTS;
+            const double yh = (double)__fadd_rn(a.y[i0 + ii], a.shift_y) * a.inv_y0;
+            double u = 0.0;
+            for (int q = D - p; q >= 0; --q) u = fma(u, yh, tc[p * (D + 1) + q]);
+            sU[p * kTS + ii] = u;
+        }
+        __syncthreads();
+    }
+    TOUT* turns = (TOUT*)a.turns + (size_t)s * a.n * a.n;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        const int j = j0 + tx * 4 + w;
+        const double xh = (double)__fadd_rn(a.x[j], a.shift_x) * a.inv_x0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int ii = ty * 4 + u;
+            double phi = acc[u][w];
+            if (D >= 0) {
+                double pl = 0.0;
+                for (int p = D; p >= 0; --p) pl = fma(pl, xh, sU[p * kTS + ii]);
+                phi += pl;
+            }
+            const size_t o = (size_t)(i0 + ii) * a.n + j;
+            if (a.turns) {
+                const double tt = phi * 0.15915494309189533576888376;
+                turns[o] = (TOUT)(tt - rint(tt));
+            }
+            if (a.phi) {
+                if (a.phi_f64) ((double*)a.phi)[(size_t)s * a.n * a.n + o] = phi;
+                else ((float*)a.phi)[(size_t)s * a.n * a.n + o] = (float)phi;
+            }
+        }
+    }
+}
+
+int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st) {
+    const int khalf = a.m - a.m_split;
+    if (khalf > 0) {
+        dim3 g((a.n + 255) / 256, khalf, a.nscreens);
+        k_screen_factors64<<<g, 256, 0, st>>>(a);
+    }
+    if (a.degree >= 0) {
+        dim3 g((a.degree + 1) * (a.degree + 1), a.nscreens);
+        k_screen_poly_coef<<<g, 128, 0, st>>>(a);
+    }
+    const int smem_gemm = 4 * kKC * kTS * (int)sizeof(double);
+    const int smem_poly = (a.degree + 1) * kTS * (int)sizeof(double);
+    const int smem = smem_gemm > smem_poly ? smem_gemm : smem_poly;
+    dim3 g(a.n / kTS, a.n / kTS, a.nscreens);
+    if (a.turns_f64) {
+        k_screen_gemm64<double><<<g, 256, smem, st>>>(a);
+    } else {
+        k_screen_gemm64<float><<<g, 256, smem, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pa

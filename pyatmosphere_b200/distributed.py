@@ -1,0 +1,97 @@
+"""Realization sharding over the GPUs of one box and the reduction of Monte-Carlo statistics.
+
+Independent realizations are the only parallel axis of this path: every batch of realizations is cut into
+G contiguous blocks of global indices, rank r takes block r, and the device RNG is keyed by the global index, so the
+records do not depend on G.  The data path has no collective; only the per-sample scalar tables (a few KB) are gathered and
+the PDT histograms / moment sums all-reduced, over NCCL on GPUs (gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _td():
+    import torch.distributed as td
+    return td
+
+
+def world_rank():
+    try:
+        td = _td()
+        if td.is_available() and td.is_initialized():
+            return td.get_world_size(), td.get_rank()
+    except ImportError:
+        pass
+    return 1, 0
+
+
+def shard_indices(first: int, count: int, rank: int, world: int) -> np.ndarray:
+    """Global realization indices in [first, first+count) owned by `rank`: contiguous blocks, sizes differing by
+    at most one (so that one launch of the device RNG, keyed by consecutive indices, serves a rank)."""
+    return np.array_split(np.arange(first, first + count, dtype=np.int64), world)[rank]
+
+
+def _comm_device():
+    import torch
+    td = _td()
+    if td.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def gather_rows(local: np.ndarray, local_rows: np.ndarray, total_rows: int) -> np.ndarray:
+    """Assemble a [total_rows][C] table on every rank from each rank's rows (`local_rows` = positions of the
+    rows of `local` in the full table).  Implemented as an all-reduce(sum) of a zero-filled table: rows are
+    disjoint, so the sum is exact and every rank gets identical bytes."""
+    world, _ = world_rank()
+    local = np.asarray(local, dtype=np.float64)
+    if world == 1:
+        out = np.zeros((total_rows, local.shape[1]), dtype=np.float64)
+        out[local_rows] = local
+        return out
+    import torch
+    td = _td()
+    full = torch.zeros((total_rows, local.shape[1]), dtype=torch.float64)
+    full[torch.as_tensor(local_rows, dtype=torch.long)] = torch.as_tensor(local)
+    full = full.to(_comm_device())
+    td.all_reduce(full, op=td.ReduceOp.SUM)
+    return full.cpu().numpy()
+
+
+def allreduce_sum(values) -> np.ndarray:
+    """Sum an integer histogram or a vector of float64 moment sums over all ranks."""
+    world, _ = world_rank()
+    arr = np.asarray(values)
+    if world == 1:
+        return arr.copy()
+    import torch
+    td = _td()
+    t = torch.as_tensor(arr).to(_comm_device())
+    td.all_reduce(t, op=td.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+def reduce_statistics(local_table: np.ndarray, columns: dict, eta_names=(), bins: int = 200):
+    """Reduce per-rank sample tables to the statistics BeamResult / PDTResult report, without gathering
+    samples: n, sum v, sum v^2 for v in {<x>^2, 4<x^2>, 4<x^2>-4<x>^2} (simulations/beam.py:35-71) and one
+    `bins`-bin histogram on [0,1] per aperture (simulations/pdt.py:30-31).  Returns a dict."""
+    t = np.asarray(local_table, dtype=np.float64).reshape(-1, max(1, len(columns)))
+    out = {}
+    if "mean_x" in columns and "mean_x2" in columns:
+        bw2 = t[:, columns["mean_x"]] ** 2
+        lt2 = 4 * t[:, columns["mean_x2"]]
+        st2 = lt2 - 4 * bw2
+        sums = np.array([len(t)] + [f(v) for v in (bw2, lt2, st2) for f in (np.sum, lambda a: np.sum(a * a))], dtype=np.float64)
+        sums = allreduce_sum(sums)
+        n = sums[0]
+        for i, name in enumerate(("bw", "lt", "st")):
+            s1, s2 = sums[1 + 2 * i], sums[2 + 2 * i]
+            mean = s1 / n
+            var = max((s2 - n * mean * mean) / (n - 1), 0.0) if n > 1 else float("nan")
+            root = np.sqrt(mean)
+            out[name] = (float(root), float(np.sqrt(var) / np.sqrt(n) / 2 / root))
+        out["count"] = int(n)
+    for name in eta_names:
+        h = np.histogram(t[:, columns[name]], bins=bins, range=(0, 1))[0].astype(np.int64)
+        out[("hist", name)] = allreduce_sum(h)
+    return out

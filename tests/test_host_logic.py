@@ -1,0 +1,218 @@
+"""CPU-only tests: host mirror of the reference API, the C-ABI surface, the planning of the ring split and the
+multi-rank reduction (gloo, world_size 2).  No compute call is made here (there is no GPU)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_golden
+from oracle import splitstep as orc
+
+import pyatmosphere_b200 as pa
+from pyatmosphere_b200 import _engine as eng
+from pyatmosphere_b200 import _native as nat
+from pyatmosphere_b200 import distributed as dist
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
+    declared = set(re.findall(r"PA_API[^;(]*?\b(pa_\w+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    assert declared == set(nat.SIGNATURES), declared ^ set(nat.SIGNATURES)
+    lib = nat.load()                       # raises if the .so was not built: there is no fallback
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pa_version() == 100
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ch = pa.QuickChannel(grid_resolution=64)
+    with pytest.raises(nat.NativeError):
+        ch.run()
+    pa.gpu.config["use_gpu"] = False
+    try:
+        with pytest.raises(pa.gpu.NoCpuPathError):
+            ch.run()
+    finally:
+        pa.gpu.config["use_gpu"] = True
+
+
+def test_public_names_match_reference_surface():
+    for name in ["Channel", "QuickChannel", "RectGrid", "RandLogPolarGrid", "GaussianSource", "IdenticalPhaseScreensPath",
+                 "PhaseScreensPath", "VacuumPath", "SSPhaseScreen", "CirclePupil", "MVKModel", "measures", "simulations", "gpu"]:
+        assert hasattr(pa, name), name
+    for name in ["I", "eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2"]:
+        assert callable(getattr(pa.measures, name))
+    for name in ["Simulation", "Measure", "Result", "BeamResult", "PDTResult", "TrackedPDTResult"]:
+        assert hasattr(pa.simulations, name)
+    assert "use_gpu" in pa.gpu.config and callable(pa.gpu.get_array) and callable(pa.gpu.get_xp)
+
+
+def test_grids_match_oracle_bitwise():
+    for n, d in [(128, 4e-3), (2048, 1.5e-3), (1024, 1e-3), (7, 0.3)]:
+        g = pa.RectGrid(n, d)
+        x, y = orc.rect_xy(n, d)
+        assert np.array_equal(g.get_x(), x) and np.array_equal(g.get_y(), y)
+        assert g.get_x().dtype == np.float32 and g.get_x().shape == (1, n) and g.get_y().shape == (n, 1)
+        assert g.origin_index == (n // 2, n // 2)
+        assert g.get_f_grid().delta == orc.f_grid_delta(n, d)
+        assert np.array_equal(g.get_rho2(), x**2 + y**2)
+    assert list(pa.RectGrid(4, 0.5).extent) == [-1.0, 1.0, -1.0, 1.0]
+    lp = pa.RandLogPolarGrid(points=2**10, f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2)
+    assert np.array_equal(lp.base, orc.logpolar_base(2**10, 1 / 1e3 / 15, 1 / 6e-3 * 2))
+
+
+def _channel(p):
+    return pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]),
+        source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=p.get("F0", np.inf)),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.SSPhaseScreen(model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
+                                          f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])),
+            length=p["length"], count=p["count"], position_in_slab=p.get("where", "middle"), losses_db=p.get("losses_db", 0)),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
+
+
+@pytest.mark.parametrize("name", ["turb128", "turb128_after_lossy", "turb64_before", "quick256"])
+def test_spectra_drawn_in_reference_order(name):
+    """np.random.seed(s) + the host mirror reproduces the coefficients the reference exported."""
+    g = load_golden(name)
+    ch = _channel(g["params"])
+    ch.path.init_phase_screens()
+    assert np.array_equal(ch.path.phase_screens[0]._get_psd(), g["psd"])
+    assert np.array_equal(np.asarray(ch.path.positions), g["positions"])
+    np.random.seed(int(g["seed"]))
+    for s, ps in enumerate(ch.path.phase_screens):
+        sp = ps._get_spectrum(False)
+        assert np.array_equal(sp.rho, g["rho"][s]) and np.array_equal(sp.theta, g["theta"][s])
+        assert np.array_equal(sp.value, g["value"][s])
+    np.random.seed(int(g["seed"]))
+    fx, fy, cf = eng.draw_spectra_numpy(ch.path, 1)
+    ofx, ofy = orc.spectrum_to_fxy(g["rho"][1], g["theta"][1])
+    assert np.array_equal(fx[0, 1], ofx.ravel()) and np.array_equal(fy[0, 1], ofy.ravel()) and np.array_equal(cf[0, 1], g["value"][1])
+
+
+def test_path_geometry_and_losses():
+    p = load_golden("turb128_after_lossy")["params"]
+    ch = _channel(p)
+    legs = ch.path.leg_lengths()
+    assert legs == orc.leg_lengths(p["length"], orc.screen_positions(p["length"], p["count"], "after"))
+    assert legs[-1] == 0.0
+    sc = eng.path_losses(ch.path, legs)
+    assert np.allclose(sc, [10 ** (-(p["losses_db"] * l / p["length"]) / 20) for l in legs[:-1]])
+    before = _channel(dict(p, where="before"))
+    lb = before.path.leg_lengths()
+    assert lb[0] == 0.0
+    # zero share falls back to the full loss (pathes.py:20)
+    assert eng.path_losses(before.path, lb)[0] == pytest.approx(10 ** (-p["losses_db"] / 20))
+    with pytest.raises(ValueError):
+        pa.IdenticalPhaseScreensPath(length=1.0, count=2, phase_screen=ch.path.phase_screen, position_in_slab="centre")
+    assert ch.get_rythov2() == pytest.approx(orc.rytov2(p["Cn2"], 2 * np.pi / p["wvl"], p["length"]))
+
+
+def test_low_ring_plan_bounds_truncation_error():
+    """The (m_split, degree) the host picks keeps the Taylor remainder of every low ring under the tolerance."""
+    g = load_golden("psd_readme")
+    base, psd = g["c3_base"], g["c3_psd"]
+    ext = 1024 * 1.5e-3
+    for theta_cut, tol in [(2.0, 1e-7), (2.0, 1e-12), (0.5, 1e-12), (6.0, 1e-7)]:
+        ms, deg = eng.plan_low_rings(base, psd, ext, ext, theta_cut, tol)
+        assert 0 < ms < len(base) and 0 < deg <= eng.MAX_DEGREE
+        t = 2 * np.pi * base[:ms].astype(np.float64) * np.hypot(ext, ext)
+        assert t.max() <= theta_cut
+        from math import factorial
+        rem = np.sum(6 * np.sqrt(psd[:ms].astype(np.float64)) * t ** (deg + 1) / factorial(deg + 1))
+        assert rem <= tol
+    assert eng.plan_low_rings(base, psd, ext, ext, 0.0, 1e-7) == (0, -1)
+    assert eng.plan_low_rings(base[::-1], psd, ext, ext, 2.0, 1e-7) == (0, -1)     # unsorted rings: no split
+    # numerically: polynomial + remaining harmonics == all harmonics (float64 numpy model of the kernel's split)
+    rng = np.random.default_rng(0)
+    m = 64
+    fx = (rng.standard_normal(m) * np.logspace(-4, 0, m)).astype(np.float32)
+    fy = (rng.standard_normal(m) * np.logspace(-4, 0, m)).astype(np.float32)
+    c = (rng.standard_normal(m) + 1j * rng.standard_normal(m)) * np.logspace(3, -1, m)
+    xs = np.linspace(-1.5, 1.5, 33)
+    full = np.real(np.sum(c[:, None, None] * np.exp(2j * np.pi * (fy[:, None, None] * xs[None, :, None] + fx[:, None, None] * xs[None, None, :])), axis=0))
+    ms, D = 40, 30
+    from math import factorial
+    poly = np.zeros_like(full)
+    for pp in range(D + 1):
+        for q in range(D + 1 - pp):
+            S = np.sum(c[:ms] * (2 * np.pi * fx[:ms].astype(np.float64)) ** pp * (2 * np.pi * fy[:ms].astype(np.float64)) ** q)
+            T = np.real(1j ** (pp + q) * S) / (factorial(pp) * factorial(q))
+            poly += T * xs[None, :] ** pp * xs[:, None] ** q
+    hi = np.real(np.sum(c[ms:, None, None] * np.exp(2j * np.pi * (fy[ms:, None, None] * xs[None, :, None] + fx[ms:, None, None] * xs[None, None, :])), axis=0))
+    assert np.max(np.abs(poly + hi - full)) < 1e-9 * np.max(np.abs(full))
+
+
+def test_simulation_tree_and_batchability():
+    p = load_golden("turb128")["params"]
+    ch = _channel(p)
+    beam = pa.simulations.BeamResult(ch, max_size=5)
+    pdt = pa.simulations.PDTResult(ch, max_size=9)
+    sim = pa.simulations.Simulation([beam, pdt])
+    assert len(list(sim.flattened_measures())) == 7
+    assert sim.batchable() and sim.remaining() == 9 and not sim.is_measures_done()
+    assert [m.name for m in beam.measures] == ["mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2", "mean_x2_r"]
+    assert pdt.measures[0].name == str(p["pupil"])
+    custom = pa.simulations.Measure(ch, "atmosphere", lambda channel, output: 0.0, name="custom", max_size=2)
+    assert not pa.simulations.Simulation([beam], [custom]).batchable()
+    cols = eng.table_columns([0.1], [0.2])
+    assert cols["mean_x"] == 1 and cols[("fixed", 0.1)] == 7 and cols[("tracked", 0.2)] == 8
+    for m in beam.measures:
+        m.data = [0.1, 0.2, 0.3, 0.4, 0.5]
+    assert beam.measures[0].is_done and sim.remaining() == 9
+    bw = beam.bw
+    want = orc.beam_statistics(beam.measures[0].data, beam.measures[2].data)
+    assert bw == pytest.approx(want["bw"]) and beam.lt == pytest.approx(want["lt"]) and beam.st == pytest.approx(want["st"])
+
+
+def test_result_csv_roundtrip(tmp_path):
+    """Same on-disk format as the reference: header = measure names, '%.3e' floats; resumed on construction."""
+    p = load_golden("turb128")["params"]
+    ch = _channel(p)
+    path = str(tmp_path / "beam.csv")
+    beam = pa.simulations.BeamResult(ch, max_size=4, save_path=path)
+    for i, m in enumerate(beam.measures):
+        m.data = [0.123456 * (i + 1), -1.5e-7 * (i + 1)]
+    beam.save_output()
+    lines = open(path).read().strip().splitlines()
+    assert lines[0] == "mean_x,mean_y,mean_x2,mean_xy,mean_y2,mean_x2_r"
+    assert lines[1].split(",")[0] == "1.235e-01" and lines[2].split(",")[1] == "-3.000e-07"
+    again = pa.simulations.BeamResult(ch, max_size=4, save_path=path)
+    assert again.measures[0].data == [0.1235, -1.5e-07] and len(again.measures[5]) == 2
+
+
+def test_pdt_histogram_binning():
+    p = load_golden("turb128")["params"]
+    ch = _channel(p)
+    pdt = pa.simulations.PDTResult(ch, max_size=10)
+    pdt.measures[0].data = [0.0, 0.004999, 0.005, 1.0, 0.9999, 0.5]
+    assert np.array_equal(pdt.histogram(), orc.pdt_histogram(pdt.measures[0].data, 200))
+
+
+def test_shard_indices_partition():
+    for first, count, world in [(0, 8, 2), (5, 7, 4), (0, 3, 8), (16, 64, 8)]:
+        parts = [dist.shard_indices(first, count, r, world) for r in range(world)]
+        assert np.array_equal(np.concatenate(parts), np.arange(first, first + count))
+        assert max(len(q) for q in parts) - min(len(q) for q in parts) <= 1
+        for q in parts:
+            assert len(q) == 0 or np.array_equal(q, np.arange(q[0], q[0] + len(q)))
+
+
+def test_two_rank_gloo_reduction():
+    """world_size 2 over gloo: gathered sample table and reduced statistics equal the single-process result."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29571", PYTHONPATH=ROOT)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "OK" in o, o
