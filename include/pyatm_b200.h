@@ -74,10 +74,12 @@ PA_API int pa_vacuum_leg(pa_ctx* ctx, void* field_dev, int batch, double length,
  * m_split / degree: rings below m_split are summed as a float64 polynomial of that total degree
  * (m_split = 0, degree = -1: every ring goes through the contraction).
  * turns_dev: [nscreens][N][N] phase/2pi reduced to [-0.5,0.5], float32 (PA_C64 ctx) or float64 (PA_C128);
- * phi_dev (optional): full phase in radians, float32 or float64 (phi_f64). */
+ * phi_dev (optional): full phase in radians, float32 or float64 (phi_f64).
+ * coef_bound: upper bound of |coef_m| over the rings m >= m_split (fp16 range control of the tensor-core
+ * method; ignored by PA_SCREEN_EXACT; <= 0 means "at most 32"). */
 PA_API int pa_screen_ss(pa_ctx* ctx, const float* fx_dev, const float* fy_dev, const float* coef_dev, int m, int m_split,
                  int degree, double shift_x, double shift_y, int nscreens, void* turns_dev, void* phi_dev,
-                 int phi_f64, int method, void* stream);
+                 int phi_f64, int method, double coef_bound, void* stream);
 
 /* pathes.py:72-73  u <- scale * exp(-i phi) * u  with phi given in turns (see pa_phase_to_turns) */
 PA_API int pa_apply_screen(pa_ctx* ctx, void* field_dev, int batch, const void* turns_dev, double scale, void* stream);
@@ -116,6 +118,7 @@ typedef struct pa_path {
     int m, m_split, degree;           /* screens, see pa_screen_ss */
     double shift_x, shift_y;
     int screen_method;
+    double coef_bound;                /* see pa_screen_ss */
     int from_field;                   /* 0: start from the Gaussian source (generated inside the first pass);
                                          1: field_dev already holds the input field in natural order */
 } pa_path;

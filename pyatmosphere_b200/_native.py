@@ -26,7 +26,7 @@ _ip = C.POINTER(C.c_int)
 class PaPath(C.Structure):
     _fields_ = [("n_screens", _int), ("leg_lengths_host", _dp), ("screen_scale_host", _dp), ("final_scale", _dbl),
                 ("wvl", _dbl), ("w0", _dbl), ("F0", _dbl), ("m", _int), ("m_split", _int), ("degree", _int),
-                ("shift_x", _dbl), ("shift_y", _dbl), ("screen_method", _int), ("from_field", _int)]
+                ("shift_x", _dbl), ("shift_y", _dbl), ("screen_method", _int), ("coef_bound", _dbl), ("from_field", _int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/pyatm_b200.h declares (checked by the tests)
@@ -42,7 +42,7 @@ SIGNATURES = {
     "pa_ctx_fft_geometry": (_int, [_vp, _vp]),
     "pa_source_gaussian": (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _vp]),
     "pa_vacuum_leg": (_int, [_vp, _vp, _int, _dbl, _dbl, _vp]),
-    "pa_screen_ss": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _dbl, _dbl, _int, _vp, _vp, _int, _int, _vp]),
+    "pa_screen_ss": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _dbl, _dbl, _int, _vp, _vp, _int, _int, _dbl, _vp]),
     "pa_apply_screen": (_int, [_vp, _vp, _int, _vp, _dbl, _vp]),
     "pa_phase_to_turns": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
     "pa_intensity": (_int, [_vp, _vp, _vp, _int, _vp]),

@@ -4,6 +4,7 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -60,6 +61,9 @@ struct pa_ctx {
     float* spec = nullptr; size_t spec_bytes = 0;        // fx | fy | coef staging for pa_simulate_batch
     float* pupils = nullptr; size_t pupils_bytes = 0;
     double* table = nullptr; size_t table_bytes = 0;
+    void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
+    int* tc_err = nullptr;
+    int num_sms = 148;
     size_t csize() const { return prec == 0 ? 8 : 16; }
     size_t rsize() const { return prec == 0 ? 4 : 8; }
 };
@@ -206,15 +210,18 @@ static void source_params(double w0, double wvl, double F0, double* amp, double*
 
 static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coef, int m, int m_split, int degree,
                    double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method,
-                   cudaStream_t st) {
+                   double coef_bound, cudaStream_t st) {
     PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called before generating screens");
     PA_REQUIRE(m > 0 && m_split >= 0 && m_split <= m, "bad m / m_split (%d, %d)", m, m_split);
     PA_REQUIRE(degree >= -1 && degree <= kMaxPolyDegree, "polynomial degree %d outside [-1, %d]", degree, kMaxPolyDegree);
     PA_REQUIRE(m_split == 0 || degree >= 0, "m_split > 0 needs degree >= 0");
-    PA_REQUIRE(method == PA_SCREEN_EXACT, "screen method %d not available in this build", method);
+    PA_REQUIRE(method == PA_SCREEN_EXACT || method == PA_SCREEN_TC, "unknown screen method %d", method);
+    PA_REQUIRE(method == PA_SCREEN_EXACT || (c->prec == PA_C64 && c->n % 256 == 0),
+               "the tensor-core screen method needs a complex64 context and a grid size that is a multiple of 256");
     const int n = c->n;
     const int k2 = 2 * (m - m_split);
-    PA_REQUIRE(c->pq_bytes >= (size_t)nscreens * (k2 > 0 ? k2 : 1) * n * sizeof(double), "screen workspace not reserved");
+    if (method == PA_SCREEN_EXACT)
+        PA_REQUIRE(c->pq_bytes >= (size_t)nscreens * (k2 > 0 ? k2 : 1) * n * sizeof(double), "screen workspace not reserved");
     ScreenLaunch a;
     a.n = n;
     a.m = m;
@@ -246,11 +253,36 @@ static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coe
     a.turns_f64 = c->prec == 1;
     a.phi = phi;
     a.phi_f64 = phi_f64;
+    a.p_scale = 1024.0;
+    if (method == PA_SCREEN_TC) {
+        // keep |P| * p_scale below 2^15 (fp16 max 65504): p_scale = 2^(15 - ceil(log2 bound)), clipped to [1, 1024]
+        const double bound = coef_bound > 0 ? coef_bound : 32.0;
+        int e = 15 - (int)ceil(log2(bound));
+        e = e < 0 ? 0 : (e > 10 ? 10 : e);
+        a.p_scale = ldexp(1.0, e);
+        const size_t need = screen_tc_workspace(n, m, m_split, nscreens);
+        PA_REQUIRE(c->tcws_bytes >= need, "tensor-core screen workspace not reserved");
+        int rc = launch_screen_poly(a, st);
+        if (rc) return check_launch(rc, "screen polynomial");
+        static const int swap = getenv("PYATM_TC_SWAP") ? atoi(getenv("PYATM_TC_SWAP")) : 0;
+        note(3);
+        return check_launch(launch_screen_tc(a, c->tcws, c->tc_err, c->num_sms, swap, st), "tensor-core screen synthesis");
+    }
     note(3);
     return check_launch(launch_screen_exact(a, st), "screen synthesis");
 }
 
-static int ensure_screen_ws(pa_ctx* c, int nscreens, int m, int m_split, int degree) {
+static int ensure_screen_ws(pa_ctx* c, int nscreens, int m, int m_split, int degree, int method) {
+    if (method == PA_SCREEN_TC) {
+        int rc = grow(&c->tcws, &c->tcws_bytes, screen_tc_workspace(c->n, m, m_split, nscreens));
+        if (rc) return rc;
+        if (!c->tc_err) {
+            PA_CUDA(cudaMalloc((void**)&c->tc_err, sizeof(int)));
+            PA_CUDA(cudaMemset(c->tc_err, 0, sizeof(int)));
+        }
+        const size_t pneed = (size_t)nscreens * (degree + 2) * (degree + 2) * sizeof(double);
+        return grow((void**)&c->polyc, &c->polyc_bytes, pneed);
+    }
     const int k2 = 2 * (m - m_split);
     const size_t need = (size_t)nscreens * (k2 > 0 ? k2 : 1) * c->n * sizeof(double);
     if (c->pq_bytes < need) {
@@ -305,6 +337,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
         return PA_ERR_CUDA;
     }
     c->htabs.reserve(256);
+    c->num_sms = prop.multiProcessorCount;
     *out = c;
     return PA_OK;
 }
@@ -312,7 +345,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
 int pa_ctx_destroy(pa_ctx* c) {
     if (!c) return PA_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table};
+    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& h : c->htabs)
@@ -373,12 +406,14 @@ int pa_vacuum_leg(pa_ctx* c, void* field, int batch, double length, double wvl, 
 }
 
 int pa_screen_ss(pa_ctx* c, const float* fx, const float* fy, const float* coef, int m, int m_split, int degree,
-                 double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method, void* stream) {
+                 double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method, double coef_bound,
+                 void* stream) {
     PA_REQUIRE(c && fx && fy && coef && nscreens > 0, "bad arguments to pa_screen_ss");
     PA_REQUIRE(turns || phi, "pa_screen_ss needs at least one output");
-    int rc = ensure_screen_ws(c, nscreens, m, m_split, degree);
+    int rc = ensure_screen_ws(c, nscreens, m, m_split, degree, method);
     if (rc) return rc;
-    return screens(c, fx, fy, coef, m, m_split, degree, shift_x, shift_y, nscreens, turns, phi, phi_f64, method, (cudaStream_t)stream);
+    return screens(c, fx, fy, coef, m, m_split, degree, shift_x, shift_y, nscreens, turns, phi, phi_f64, method, coef_bound,
+                   (cudaStream_t)stream);
 }
 
 int pa_apply_screen(pa_ctx* c, void* field, int batch, const void* turns, double scale, void* stream) {
@@ -482,7 +517,7 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
     const int S = p->n_screens, n = c->n;
     int rc;
     if (S > 0) {
-        rc = ensure_screen_ws(c, batch, p->m, p->m_split, p->degree);
+        rc = ensure_screen_ws(c, batch, p->m, p->m_split, p->degree, p->screen_method);
         if (rc) return rc;
         rc = grow(&c->turns, &c->turns_bytes, (size_t)batch * n * n * c->rsize());
         if (rc) return rc;
@@ -504,7 +539,7 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
     auto gen_screen = [&](int i) -> int {   // coefficient arrays are [S][batch][m]: one contiguous slab per path position
         const size_t o = (size_t)i * batch * p->m;
         return screens(c, fx + o, fy + o, coef + 2 * o, p->m, p->m_split, p->degree, p->shift_x, p->shift_y, batch, c->turns,
-                       nullptr, 0, p->screen_method, st);
+                       nullptr, 0, p->screen_method, p->coef_bound, st);
     };
 
     for (int i = 0; i < S; ++i) {

@@ -26,9 +26,13 @@ struct ScreenLaunch {
     int turns_f64;
     void* phi;          // out, optional full phase [nscreens][n][n] float or double
     int phi_f64;
+    double p_scale;     // tensor-core path: power-of-two scale of the P operand (fp16 range)
 };
 
 int screen_init_constants();
 int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st);
+int launch_screen_poly(const ScreenLaunch& a, cudaStream_t st);
+size_t screen_tc_workspace(int n, int m, int m_split, int nscreens);
+int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st);
 
 }  // namespace pa

@@ -203,6 +203,14 @@ __global__ void __launch_bounds__(256) k_screen_gemm64(ScreenLaunch a) {
     }
 }
 
+int launch_screen_poly(const ScreenLaunch& a, cudaStream_t st) {
+    if (a.degree >= 0) {
+        dim3 g((a.degree + 1) * (a.degree + 1), a.nscreens);
+        k_screen_poly_coef<<<g, 128, 0, st>>>(a);
+    }
+    return (int)cudaGetLastError();
+}
+
 int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st) {
     const int khalf = a.m - a.m_split;
     if (khalf > 0) {

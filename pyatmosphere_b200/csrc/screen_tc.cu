@@ -1,0 +1,370 @@
+// Tensor-core phase-screen synthesis for sm_100a: tcgen05.mma (kind::f16, fp32 accumulators in TMEM) fed by
+// cp.async.bulk (TMA engine) through an mbarrier pipeline, with a float64 epilogue.
+//
+//   phi_hi[i][j] = sum_k P[k][i] Q[k][j]      (rings >= m_split; K2 = 2 (M - m_split) rows, see screen.cu)
+//
+// Precision: every operand is split into two fp16 numbers, v * s = hi + lo (s a power of two: 2^10 for P,
+// 2^4 for Q; lo may be subnormal), and  D += Ph Qh + Ph Ql + Pl Qh  is accumulated in ONE fp32 TMEM accumulator.
+// The dropped Pl Ql term is 2^-22 relative.  Rings are fed in DESCENDING order of radius so that the running sum
+// stays small until the last chunks (the variance per ring falls like f^-5/3): with round-toward-zero
+// accumulation this keeps the error at ~2e-6 rad rms for the README channel (measured: tests/test_gpu_screen_tc.py;
+// CPU model: DESIGN.md "screen precision").
+//
+// Tiling: one CTA = 128 (i) x 256 (j) output tile, K chunks of 32, 3 smem stages of 48 KB, two TMEM accumulator
+// buffers of 256 columns so that the float64 epilogue of tile t overlaps the MMAs of tile t+1.
+// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane = row).
+// Operands are pre-tiled in global memory by k_factors_tc in the canonical K-major / no-swizzle UMMA layout
+// (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "internal_screen.h"
+
+namespace pa {
+namespace tc {
+
+constexpr int TM = 128, TN = 256, BK = 32, STAGES = 3;
+constexpr int P_HALF = TM * BK * 2;            // bytes of one fp16 operand block (hi or lo)
+constexpr int Q_HALF = TN * BK * 2;
+constexpr int P_STAGE = 2 * P_HALF;            // 16 KiB
+constexpr int Q_STAGE = 2 * Q_HALF;            // 32 KiB
+constexpr int STAGE_BYTES = P_STAGE + Q_STAGE;
+constexpr int THREADS = 256;
+constexpr float Q_SCALE = 16.0f;     // P is scaled by a.p_scale (power of two chosen on the host from the coefficient bound)
+constexpr uint32_t SPIN_LIMIT = 1u << 28;
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    atomicExch(err, 1);     // never spin for ever on the GPU box: flag and abort the kernel
+    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell); layout_type = 0 (no swizzle)
+    return d;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// instruction descriptor: fp32 accumulate, fp16 A and B, both K-major, M = 128, N = 256
+constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+
+// ---- operand generation -----------------------------------------------------------------------------------
+// Global layout (fp16): P: [screen][row block i/128][k block k/32]{hi,lo}[k chunk (k%32)/8][row group (i%128)/8][i%8][k%8]
+//                       Q: [screen][col block j/256][k block k/32]{hi,lo}[k chunk][col group (j%256)/8][j%8][k%8]
+// k = 2 r + {0,1} for ring rank r, where rank r is ring  m - 1 - r  (descending radius); ranks beyond the last
+// high ring are zero padding up to a multiple of 16 ranks (32 k).
+// One thread = one (row or column) x one k chunk of 8 = 4 rings.  grid: (n/128, kchunks, 2*nscreens), block 128.
+struct Split { __half hi, lo; };
+__device__ __forceinline__ Split split16(double v) {
+    Split s;
+    s.hi = __double2half(v);
+    s.lo = __double2half(v - (double)__half2float(s.hi));
+    return s;
+}
+
+__global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, __half* Q, int kpad) {
+    const int idx = blockIdx.x * 128 + threadIdx.x;           // row i (P) or column j (Q)
+    const int chunk = blockIdx.y;                              // k chunk of 8
+    const bool is_q = (blockIdx.z & 1) != 0;
+    const int s = blockIdx.z >> 1;
+    const int nhigh = a.m - a.m_split;
+    const double coord = is_q ? (double)__fadd_rn(a.x[idx], a.shift_x) : (double)__fadd_rn(a.y[idx], a.shift_y);
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int rank = chunk * 4 + q;
+        double v0 = 0.0, v1 = 0.0;
+        if (rank < nhigh) {
+            const int m = a.m - 1 - rank;
+            const size_t o = (size_t)s * a.m + m;
+            double sn, cs;
+            sincospi(2.0 * (coord * (double)(is_q ? a.fx[o] : a.fy[o])), &sn, &cs);
+            if (is_q) {
+                v0 = cs * (double)Q_SCALE;
+                v1 = sn * (double)Q_SCALE;
+            } else {
+                const float2 c = a.coef[o];
+                v0 = ((double)c.x * cs - (double)c.y * sn) * a.p_scale;
+                v1 = -((double)c.x * sn + (double)c.y * cs) * a.p_scale;
+            }
+        }
+        const Split s0 = split16(v0), s1 = split16(v1);
+        hi[2 * q] = s0.hi; hi[2 * q + 1] = s1.hi;
+        lo[2 * q] = s0.lo; lo[2 * q + 1] = s1.lo;
+    }
+    const int tile = is_q ? TN : TM;
+    const int half_bytes = is_q ? Q_HALF : P_HALF;
+    const int nblk = a.n / tile;
+    const int blk = idx / tile, within = idx % tile;
+    const int kb = chunk / 4, kc = chunk % 4;
+    __half* base = is_q ? Q : P;
+    char* dst = (char*)base + (((size_t)s * nblk + blk) * (kpad / BK) + kb) * (size_t)(2 * half_bytes) +
+                (size_t)kc * (tile / 8) * 128 + (size_t)(within / 8) * 128 + (within % 8) * 16;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + half_bytes) = *reinterpret_cast<const uint4*>(lo);
+}
+
+// ---- contraction + epilogue ---------------------------------------------------------------------------------
+struct TcArgs {
+    ScreenLaunch a;
+    const __half* P;
+    const __half* Q;
+    int kblocks;        // kpad / 32
+    int total_tiles;    // nscreens * (n/128) * (n/256)
+    int swap_lbo_sbo;   // debug switch for the descriptor convention
+    int* err;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const ScreenLaunch& a = g.a;
+    unsigned char* stage_base = smem;                                        // STAGES * STAGE_BYTES
+    double* sU = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);     // [(D+1)][128]
+    const int D = a.degree;
+    const double out_scale = 1.0 / (a.p_scale * (double)Q_SCALE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (size_t)(kMaxPolyDegree + 1) * TM * sizeof(double));
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 4);        // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    } else if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n = a.n;
+    const int rblocks = n / TM, cblocks = n / TN;
+    const int tiles_per_screen = rblocks * cblocks;
+
+    if (warp == 0) {
+        // ===== producer: one bulk copy per operand and stage =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+                const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
+                const int rb = rem / cblocks, cb = rem % cblocks;
+                const char* psrc = (const char*)g.P + ((size_t)s * rblocks + rb) * g.kblocks * (size_t)P_STAGE;
+                const char* qsrc = (const char*)g.Q + ((size_t)s * cblocks + cb) * g.kblocks * (size_t)Q_STAGE;
+                for (int kb = 0; kb < g.kblocks; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1, g.err);
+                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
+                    const uint32_t dst = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                    bulk_g2s(dst, psrc + (size_t)kb * P_STAGE, P_STAGE, full_bar(stage));
+                    bulk_g2s(dst + P_STAGE, qsrc + (size_t)kb * Q_STAGE, Q_STAGE, full_bar(stage));
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            const uint32_t p_lbo = g.swap_lbo_sbo ? 128u : (uint32_t)(TM / 8) * 128u, p_sbo = g.swap_lbo_sbo ? (uint32_t)(TM / 8) * 128u : 128u;
+            const uint32_t q_lbo = g.swap_lbo_sbo ? 128u : (uint32_t)(TN / 8) * 128u, q_sbo = g.swap_lbo_sbo ? (uint32_t)(TN / 8) * 128u : 128u;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+                const int buf = it & 1;
+                mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);     // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
+                for (int kb = 0; kb < g.kblocks; ++kb) {
+                    mbar_wait(full_bar(stage), phase, g.err);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                    const uint32_t sq = sp + P_STAGE;
+#pragma unroll
+                    for (int k16 = 0; k16 < BK / 16; ++k16) {
+                        const uint32_t poff = (uint32_t)k16 * 2u * (TM / 8) * 128u, qoff = (uint32_t)k16 * 2u * (TN / 8) * 128u;
+                        const uint64_t ah = umma_desc(sp + poff, p_lbo, p_sbo), al = umma_desc(sp + P_HALF + poff, p_lbo, p_sbo);
+                        const uint64_t bh = umma_desc(sq + qoff, q_lbo, q_sbo), bl = umma_desc(sq + Q_HALF + qoff, q_lbo, q_sbo);
+                        umma_f16(d_tmem, al, bh, IDESC, (kb | k16) != 0);
+                        umma_f16(d_tmem, ah, bl, IDESC, 1);
+                        umma_f16(d_tmem, ah, bh, IDESC, 1);
+                    }
+                    umma_commit(empty_bar(stage));       // smem slot free once these MMAs have read it
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(buf));             // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM lane = output row; float64 polynomial + reduction to turns =====
+        const int ew = warp & 3;
+        const int row_in_tile = ew * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
+            const int rb = rem / cblocks, cb = rem % cblocks;
+            const int i = rb * TM + row_in_tile;
+            const int j0 = cb * TN;
+            // per-row polynomial coefficients U_p(yh_i) = sum_q T_pq yh^q (only this thread reads its column of sU)
+            if (D >= 0) {
+                const double* tcf = a.polyc + (size_t)s * (D + 1) * (D + 1);
+                const double yh = (double)__fadd_rn(a.y[i], a.shift_y) * a.inv_y0;
+                for (int p = 0; p <= D; ++p) {
+                    double u = 0.0;
+                    for (int q = D - p; q >= 0; --q) u = fma(u, yh, __ldg(tcf + p * (D + 1) + q));
+                    sU[p * TM + row_in_tile] = u;
+                }
+            }
+            const int buf = it & 1;
+            mbar_wait(tfull_bar(buf), (it >> 1) & 1, g.err);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TN;
+            float* turns = a.turns ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
+            for (int c0 = 0; c0 < TN; c0 += 8) {
+                float acc[8];
+                tmem_ld8(t_row + (uint32_t)c0, acc);
+                double xh[8], pl[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    xh[c] = (double)__fadd_rn(__ldg(a.x + j0 + c0 + c), a.shift_x) * a.inv_x0;
+                    pl[c] = 0.0;
+                }
+                for (int p = D; p >= 0; --p) {
+                    const double u = sU[p * TM + row_in_tile];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u);
+                }
+                float tv[8];
+                double ph[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    ph[c] = fma((double)acc[c], out_scale, pl[c]);
+                    const double tt = ph[c] * 0.15915494309189533576888376;
+                    tv[c] = (float)(tt - rint(tt));
+                }
+                if (turns) {
+                    *reinterpret_cast<float4*>(turns + c0) = make_float4(tv[0], tv[1], tv[2], tv[3]);
+                    *reinterpret_cast<float4*>(turns + c0 + 4) = make_float4(tv[4], tv[5], tv[6], tv[7]);
+                }
+                if (a.phi) {
+                    const size_t o = ((size_t)s * n + i) * n + j0 + c0;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (a.phi_f64) ((double*)a.phi)[o + c] = ph[c];
+                        else ((float*)a.phi)[o + c] = (float)ph[c];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(buf));
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (kMaxPolyDegree + 1) * TM * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
+
+}  // namespace tc
+
+// workspace requirement of the tensor-core path, in bytes, for `nscreens` screens
+size_t screen_tc_workspace(int n, int m, int m_split, int nscreens) {
+    const int nhigh = m - m_split;
+    const int kpad = ((2 * nhigh + tc::BK - 1) / tc::BK) * tc::BK;
+    return (size_t)nscreens * 2 /*P,Q*/ * 2 /*hi,lo*/ * n * (size_t)(kpad > 0 ? kpad : tc::BK) * sizeof(__half);
+}
+
+int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st) {
+    using namespace tc;
+    if (a.n % TN != 0) return (int)cudaErrorInvalidValue;
+    const int nhigh = a.m - a.m_split;
+    int kpad = ((2 * nhigh + BK - 1) / BK) * BK;
+    if (kpad == 0) kpad = BK;
+    __half* P = (__half*)workspace;
+    __half* Q = P + (size_t)a.nscreens * 2 * a.n * kpad;
+    dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
+    k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(k_screen_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_done = true;
+    }
+    TcArgs g;
+    g.a = a;
+    g.P = P;
+    g.Q = Q;
+    g.kblocks = kpad / BK;
+    g.total_tiles = a.nscreens * (a.n / TM) * (a.n / TN);
+    g.swap_lbo_sbo = swap;
+    g.err = err_flag;
+    const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
+    k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pa

@@ -120,7 +120,8 @@ class SSPhaseScreen(PhaseScreen):
         nat.check(ctx.lib.pa_screen_ss(ctx.handle, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(c_d), m, m_split, degree,
                                        float(shift[0]), float(shift[1]), 1, nat.ptr(turns), nat.ptr(phi),
                                        1 if ctx.precision == nat.PA_C128 else 0,
-                                       eng.SCREEN_METHODS[gpu.config["screen_method"]], nat.stream_ptr()))
+                                       eng.SCREEN_METHODS[gpu.config["screen_method"]],
+                                       float(np.max(np.abs(coef[m_split:]))) if m_split < m else 1.0, nat.stream_ptr()))
         return turns, phi
 
     def generate_phase_screen(self, shift: Tuple[float, float] = (0, 0), wind: bool = False, real_only: bool = False):
