@@ -172,7 +172,7 @@ def run_gpu(args):
     if world > 1:
         import torch.distributed as td
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method=args.screen_method, rng="philox", seed=1234)
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method=args.screen_method, theta_cut=None, rng="philox", seed=1234)
     p = C3
     ch = pa.Channel(
         grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
@@ -350,7 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--screen-method", dest="screen_method", default="exact")
+    ap.add_argument("--screen-method", dest="screen_method", default="auto")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-warm", action="store_true")
     args = ap.parse_args()

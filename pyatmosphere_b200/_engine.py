@@ -11,6 +11,23 @@ from . import _native as nat
 from . import gpu
 
 SCREEN_METHODS = {"exact": nat.PA_SCREEN_EXACT, "tc": nat.PA_SCREEN_TC}
+
+
+def screen_method(n: int) -> int:
+    """Resolve gpu.config['screen_method'] for a grid of size n."""
+    name = gpu.config["screen_method"]
+    if name == "auto":
+        name = "tc" if (gpu.precision() == 0 and n % 256 == 0) else "exact"
+    if name == "tc" and (gpu.precision() != 0 or n % 256 != 0):
+        raise ValueError("screen_method 'tc' needs dtype complex64 and a grid size that is a multiple of 256")
+    return SCREEN_METHODS[name]
+
+
+def theta_cut(n: int) -> float:
+    tc = gpu.config["theta_cut"]
+    if tc is None:
+        return 10.0 if screen_method(n) == nat.PA_SCREEN_TC else 2.0
+    return float(tc)
 MAX_DEGREE = 63
 
 

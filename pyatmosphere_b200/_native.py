@@ -9,7 +9,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpyatm_b200.so")
+LIB_PATH = os.environ.get("PYATM_LIB", os.path.join(_HERE, "libpyatm_b200.so"))
 
 PA_C64, PA_C128 = 0, 1
 PA_SCREEN_EXACT, PA_SCREEN_TC = 0, 1

@@ -15,11 +15,11 @@ import sys
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
-OBJ = os.path.join(CSRC, "_build")
-LIB = os.path.join(PKG, "libpyatm_b200.so")
+OBJ = os.path.join(CSRC, os.environ.get("PYATM_OBJ_DIR", "_build"))
+LIB = os.environ.get("PYATM_LIB", os.path.join(PKG, "libpyatm_b200.so"))      # override: experimental variants
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + os.environ.get("PYATM_NVCC_FLAGS", "").split()
 
 
 def _deps_mtime():

@@ -196,13 +196,50 @@ template <int N, int E, int S> __device__ __forceinline__ int reg_pos(int t, int
 }
 
 // ---- shared-memory exchange from the distribution of stage SA to that of stage SB --------------------------
+// A stage with SIGMA == 1 owns runs of R consecutive positions: with a contiguous address map (rows) and
+// complex64 data these are moved as 128-bit accesses (two elements), which is what the row swizzle is
+// conflict-free for (tools/bank_sim.py).
+template <typename T, int N, int E, int S, typename Addr>
+__device__ __forceinline__ void smem_put(const cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
+    using St = Stage<N, E, S>;
+    if constexpr (Addr::kContiguous && St::SIGMA == 1 && sizeof(cplx<T>) == 8 && St::R % 2 == 0) {
+#pragma unroll
+        for (int g = 0; g < St::G; ++g) {
+            const int base = St::base(t, g);
+#pragma unroll
+            for (int j = 0; j < St::R; j += 2)
+                *reinterpret_cast<float4*>(sm + addr(base + j)) =
+                    make_float4(v[g * St::R + j].x, v[g * St::R + j].y, v[g * St::R + j + 1].x, v[g * St::R + j + 1].y);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) sm[addr(reg_pos<N, E, S>(t, i))] = v[i];
+    }
+}
+template <typename T, int N, int E, int S, typename Addr>
+__device__ __forceinline__ void smem_get(cplx<T> (&v)[E], int t, const cplx<T>* sm, const Addr& addr) {
+    using St = Stage<N, E, S>;
+    if constexpr (Addr::kContiguous && St::SIGMA == 1 && sizeof(cplx<T>) == 8 && St::R % 2 == 0) {
+#pragma unroll
+        for (int g = 0; g < St::G; ++g) {
+            const int base = St::base(t, g);
+#pragma unroll
+            for (int j = 0; j < St::R; j += 2) {
+                const float4 q = *reinterpret_cast<const float4*>(sm + addr(base + j));
+                v[g * St::R + j] = mkc<T>(q.x, q.y);
+                v[g * St::R + j + 1] = mkc<T>(q.z, q.w);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = sm[addr(reg_pos<N, E, S>(t, i))];
+    }
+}
 template <typename T, int N, int E, int SA, int SB, typename Addr>
 __device__ __forceinline__ void exchange(cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
-#pragma unroll
-    for (int i = 0; i < E; ++i) sm[addr(reg_pos<N, E, SA>(t, i))] = v[i];
+    smem_put<T, N, E, SA>(v, t, sm, addr);
     __syncthreads();
-#pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = sm[addr(reg_pos<N, E, SB>(t, i))];
+    smem_get<T, N, E, SB>(v, t, sm, addr);
 }
 
 // ---- whole transforms on registers ------------------------------------------------------------------------

@@ -27,10 +27,12 @@ template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
 }
 
 template <int N, int E> struct RowAddr {
+    static constexpr bool kContiguous = true;
     int base;
     __device__ __forceinline__ int operator()(int p) const { return base + swz_row<N, E>(p); }
 };
 template <int N, int E, int TC> struct ColAddr {
+    static constexpr bool kContiguous = false;
     int c;
     __device__ __forceinline__ int operator()(int p) const { return swz_col<N, E, TC>(p) * TC + c; }
 };

@@ -6,7 +6,10 @@
 namespace pa {
 
 // elements per thread of the register FFT, per precision (0 = complex64, 1 = complex128)
-constexpr int kE32 = 16;
+#ifndef PA_E32
+#define PA_E32 16
+#endif
+constexpr int kE32 = PA_E32;
 constexpr int kE64 = 8;
 inline int elems_per_thread(int prec) { return prec == 0 ? kE32 : kE64; }
 

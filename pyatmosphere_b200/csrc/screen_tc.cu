@@ -12,7 +12,9 @@
 //
 // Tiling: one CTA = 128 (i) x 256 (j) output tile, K chunks of 32, 3 smem stages of 48 KB, two TMEM accumulator
 // buffers of 256 columns so that the float64 epilogue of tile t overlaps the MMAs of tile t+1.
-// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM lane = row).
+// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..19 = epilogue (TMEM lane = row; the
+// four warps of a lane quarter split the 256 columns).  The per-row polynomial coefficients U_p(yh_i) come from
+// k_poly_rows (one small launch per batch of screens).
 // Operands are pre-tiled in global memory by k_factors_tc in the canonical K-major / no-swizzle UMMA layout
 // (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
 #include <cuda_fp16.h>
@@ -29,7 +31,9 @@ constexpr int Q_HALF = TN * BK * 2;
 constexpr int P_STAGE = 2 * P_HALF;            // 16 KiB
 constexpr int Q_STAGE = 2 * Q_HALF;            // 32 KiB
 constexpr int STAGE_BYTES = P_STAGE + Q_STAGE;
-constexpr int THREADS = 256;
+constexpr int EPI_WARPS = 16;                 // four per TMEM lane quarter, each takes a quarter of the columns
+constexpr int EPI_COLS = TN / (EPI_WARPS / 4);
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr float Q_SCALE = 16.0f;     // P is scaled by a.p_scale (power of two chosen on the host from the coefficient bound)
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
@@ -46,6 +50,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err) {
     uint32_t ok = 0;
+#pragma unroll 1
     for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
         asm volatile(
             "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
@@ -100,11 +105,13 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)
 // k = 2 r + {0,1} for ring rank r, where rank r is ring  m - 1 - r  (descending radius); ranks beyond the last
 // high ring are zero padding up to a multiple of 16 ranks (32 k).
 // One thread = one (row or column) x one k chunk of 8 = 4 rings.  grid: (n/128, kchunks, 2*nscreens), block 128.
+// The phase argument is reduced exactly in float64 (coord and frequency are float32, so their product is exact
+// in float64), then the trigonometry and the scaling run in float32: the operands only carry 22 bits (hi + lo).
 struct Split { __half hi, lo; };
-__device__ __forceinline__ Split split16(double v) {
+__device__ __forceinline__ Split split16(float v) {
     Split s;
-    s.hi = __double2half(v);
-    s.lo = __double2half(v - (double)__half2float(s.hi));
+    s.hi = __float2half_rn(v);
+    s.lo = __float2half_rn(v - __half2float(s.hi));
     return s;
 }
 
@@ -115,24 +122,27 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
     const int s = blockIdx.z >> 1;
     const int nhigh = a.m - a.m_split;
     const double coord = is_q ? (double)__fadd_rn(a.x[idx], a.shift_x) : (double)__fadd_rn(a.y[idx], a.shift_y);
+    const float pscale = (float)a.p_scale;
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
         const int rank = chunk * 4 + q;
-        double v0 = 0.0, v1 = 0.0;
+        float v0 = 0.f, v1 = 0.f;
         if (rank < nhigh) {
             const int m = a.m - 1 - rank;
             const size_t o = (size_t)s * a.m + m;
-            double sn, cs;
-            sincospi(2.0 * (coord * (double)(is_q ? a.fx[o] : a.fy[o])), &sn, &cs);
+            double turns = coord * (double)(is_q ? a.fx[o] : a.fy[o]);
+            turns -= rint(turns);
+            float sn, cs;
+            sincospif(2.0f * (float)turns, &sn, &cs);
             if (is_q) {
-                v0 = cs * (double)Q_SCALE;
-                v1 = sn * (double)Q_SCALE;
+                v0 = cs * Q_SCALE;
+                v1 = sn * Q_SCALE;
             } else {
                 const float2 c = a.coef[o];
-                v0 = ((double)c.x * cs - (double)c.y * sn) * a.p_scale;
-                v1 = -((double)c.x * sn + (double)c.y * cs) * a.p_scale;
+                v0 = (c.x * cs - c.y * sn) * pscale;
+                v1 = -(c.x * sn + c.y * cs) * pscale;
             }
         }
         const Split s0 = split16(v0), s1 = split16(v1);
@@ -151,6 +161,28 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
     *reinterpret_cast<uint4*>(dst + half_bytes) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// ---- per-row polynomial coefficients: U[s][p][i] = sum_{q <= D-p} T_pq yh_i^q ---------------------------------
+// grid: (n/128, nscreens), block 128; four p at a time so that the Horner chains overlap.
+__global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U) {
+    const int D = a.degree;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int s = blockIdx.y;
+    const double* tcf = a.polyc + (size_t)s * (D + 1) * (D + 1);
+    const double yh = (double)__fadd_rn(a.y[i], a.shift_y) * a.inv_y0;
+    double* out = U + (size_t)s * (D + 1) * a.n + i;
+    for (int p0 = 0; p0 <= D; p0 += 4) {
+        double u[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int q = D - p0; q >= 0; --q) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t)
+                if (p0 + t <= D && q <= D - (p0 + t)) u[t] = fma(u[t], yh, __ldg(tcf + (p0 + t) * (D + 1) + q));
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+            if (p0 + t <= D) out[(size_t)(p0 + t) * a.n] = u[t];
+    }
+}
+
 // ---- contraction + epilogue ---------------------------------------------------------------------------------
 struct TcArgs {
     ScreenLaunch a;
@@ -158,18 +190,20 @@ struct TcArgs {
     const __half* Q;
     int kblocks;        // kpad / 32
     int total_tiles;    // nscreens * (n/128) * (n/256)
-    int swap_lbo_sbo;   // debug switch for the descriptor convention
+    int swap_lbo_sbo;   // debug bits: 1 = swap LBO/SBO, 2 = no bulk copies, 4 = no MMAs, 8 = no epilogue math (timing experiments)
     int* err;
+    const double* U;    // [nscreens][degree+1][n]: U_p(yh_i) = sum_q T_pq yh_i^q
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const ScreenLaunch& a = g.a;
     unsigned char* stage_base = smem;                                        // STAGES * STAGE_BYTES
-    double* sU = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);     // [(D+1)][128]
+    double* sU = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);     // [(D+1)][128] row coefficients of this tile
+    double* sX = sU + (size_t)(kMaxPolyDegree + 1) * TM;                      // [256] normalised column coordinates
     const int D = a.degree;
     const double out_scale = 1.0 / (a.p_scale * (double)Q_SCALE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + (size_t)(kMaxPolyDegree + 1) * TM * sizeof(double));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + ((size_t)(kMaxPolyDegree + 1) * TM + TN) * sizeof(double));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +220,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 4);        // one arrival per epilogue warp
+            mbar_init(tempty_bar(b), EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == 2) {
@@ -214,10 +248,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 const char* qsrc = (const char*)g.Q + ((size_t)s * cblocks + cb) * g.kblocks * (size_t)Q_STAGE;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1, g.err);
+                    if (g.swap_lbo_sbo & 2) {
+                        mbar_arrive(full_bar(stage));
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                        continue;
+                    }
                     mbar_expect_tx(full_bar(stage), STAGE_BYTES);
                     const uint32_t dst = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
-                    bulk_g2s(dst, psrc + (size_t)kb * P_STAGE, P_STAGE, full_bar(stage));
-                    bulk_g2s(dst + P_STAGE, qsrc + (size_t)kb * Q_STAGE, Q_STAGE, full_bar(stage));
+                    constexpr int CH = 8192;      // several 8 KiB copies in flight instead of two large ones
+#pragma unroll
+                    for (int o = 0; o < P_STAGE; o += CH) bulk_g2s(dst + o, psrc + (size_t)kb * P_STAGE + o, CH, full_bar(stage));
+#pragma unroll
+                    for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -228,8 +270,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            const uint32_t p_lbo = g.swap_lbo_sbo ? 128u : (uint32_t)(TM / 8) * 128u, p_sbo = g.swap_lbo_sbo ? (uint32_t)(TM / 8) * 128u : 128u;
-            const uint32_t q_lbo = g.swap_lbo_sbo ? 128u : (uint32_t)(TN / 8) * 128u, q_sbo = g.swap_lbo_sbo ? (uint32_t)(TN / 8) * 128u : 128u;
+            const uint32_t p_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(TM / 8) * 128u, p_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(TM / 8) * 128u : 128u;
+            const uint32_t q_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(TN / 8) * 128u, q_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(TN / 8) * 128u : 128u;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
                 mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);     // epilogue has drained this accumulator
@@ -242,6 +284,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     const uint32_t sq = sp + P_STAGE;
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
+                        if (g.swap_lbo_sbo & 4) break;
                         const uint32_t poff = (uint32_t)k16 * 2u * (TM / 8) * 128u, qoff = (uint32_t)k16 * 2u * (TN / 8) * 128u;
                         const uint64_t ah = umma_desc(sp + poff, p_lbo, p_sbo), al = umma_desc(sp + P_HALF + poff, p_lbo, p_sbo);
                         const uint64_t bh = umma_desc(sq + qoff, q_lbo, q_sbo), bl = umma_desc(sq + Q_HALF + qoff, q_lbo, q_sbo);
@@ -257,40 +300,53 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         }
     } else if (warp >= 4) {
         // ===== epilogue: TMEM lane = output row; float64 polynomial + reduction to turns =====
-        const int ew = warp & 3;
+        const int ew = warp & 3;                       // TMEM lane quarter this warp may read
+        const int cq = (warp - 4) >> 2;                // which share of the 256 columns
+        const int et = threadIdx.x - 128;              // index among the epilogue threads
         const int row_in_tile = ew * 32 + lane;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
             const int rb = rem / cblocks, cb = rem % cblocks;
             const int i = rb * TM + row_in_tile;
-            const int j0 = cb * TN;
-            // per-row polynomial coefficients U_p(yh_i) = sum_q T_pq yh^q (only this thread reads its column of sU)
-            if (D >= 0) {
-                const double* tcf = a.polyc + (size_t)s * (D + 1) * (D + 1);
-                const double yh = (double)__fadd_rn(a.y[i], a.shift_y) * a.inv_y0;
-                for (int p = 0; p <= D; ++p) {
-                    double u = 0.0;
-                    for (int q = D - p; q >= 0; --q) u = fma(u, yh, __ldg(tcf + p * (D + 1) + q));
-                    sU[p * TM + row_in_tile] = u;
-                }
-            }
+            const int j0 = cb * TN + cq * EPI_COLS;
+            const double* U = g.U + (size_t)s * (D + 1) * n + i;       // U[p * n]: coalesced over the lanes of a warp
+            // stage this tile's row coefficients in shared memory (the two warps of a row quarter take alternate p)
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");     // previous tile's readers are done
+            for (int p = cq; p <= D; p += EPI_WARPS / 4) sU[p * TM + row_in_tile] = __ldg(U + (size_t)p * n);
+            if (et < TN) sX[et] = (double)__fadd_rn(__ldg(a.x + cb * TN + et), a.shift_x) * a.inv_x0;
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+            const double* su = sU + row_in_tile;
             const int buf = it & 1;
             mbar_wait(tfull_bar(buf), (it >> 1) & 1, g.err);
             tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)buf * TN;
+            const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + cq * EPI_COLS);
+            const double* sx = sX + cq * EPI_COLS;
             float* turns = a.turns ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
-            for (int c0 = 0; c0 < TN; c0 += 8) {
+            for (int c0 = 0; c0 < EPI_COLS; c0 += 8) {
+                if (g.swap_lbo_sbo & 8) break;
                 float acc[8];
                 tmem_ld8(t_row + (uint32_t)c0, acc);
                 double xh[8], pl[8];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    xh[c] = (double)__fadd_rn(__ldg(a.x + j0 + c0 + c), a.shift_x) * a.inv_x0;
+                    xh[c] = sx[c0 + c];
                     pl[c] = 0.0;
                 }
-                for (int p = D; p >= 0; --p) {
-                    const double u = sU[p * TM + row_in_tile];
+                int p = D;
+                for (; p >= 3; p -= 4) {                 // Horner in xh, four coefficients prefetched per round
+                    const double u0 = su[p * TM], u1 = su[(p - 1) * TM], u2 = su[(p - 2) * TM], u3 = su[(p - 3) * TM];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u1);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u2);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u3);
+                }
+                for (; p >= 0; --p) {
+                    const double u = su[p * TM];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) pl[c] = fma(pl[c], xh[c], u);
                 }
@@ -327,7 +383,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     }
 }
 
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (kMaxPolyDegree + 1) * TM * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ((kMaxPolyDegree + 1) * TM + TN) * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
 
 }  // namespace tc
 
@@ -335,7 +391,8 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (kMaxPolyDegree + 1) * TM * (i
 size_t screen_tc_workspace(int n, int m, int m_split, int nscreens) {
     const int nhigh = m - m_split;
     const int kpad = ((2 * nhigh + tc::BK - 1) / tc::BK) * tc::BK;
-    return (size_t)nscreens * 2 /*P,Q*/ * 2 /*hi,lo*/ * n * (size_t)(kpad > 0 ? kpad : tc::BK) * sizeof(__half);
+    return (size_t)nscreens * 2 /*P,Q*/ * 2 /*hi,lo*/ * n * (size_t)(kpad > 0 ? kpad : tc::BK) * sizeof(__half) +
+           (size_t)nscreens * (kMaxPolyDegree + 1) * n * sizeof(double);      // + U table
 }
 
 int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st) {
@@ -346,8 +403,13 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     if (kpad == 0) kpad = BK;
     __half* P = (__half*)workspace;
     __half* Q = P + (size_t)a.nscreens * 2 * a.n * kpad;
+    double* U = reinterpret_cast<double*>(Q + (size_t)a.nscreens * 2 * a.n * kpad);
     dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
     k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
+    if (a.degree >= 0) {
+        dim3 gu(a.n / 128, a.nscreens);
+        k_poly_rows<<<gu, 128, 0, st>>>(a, U);
+    }
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(k_screen_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
@@ -362,6 +424,7 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     g.total_tiles = a.nscreens * (a.n / TM) * (a.n / TN);
     g.swap_lbo_sbo = swap;
     g.err = err_flag;
+    g.U = U;
     const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
     k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
     return (int)cudaGetLastError();

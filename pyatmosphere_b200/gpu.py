@@ -7,8 +7,10 @@ entry points raise (use the reference itself for CPU runs).
 
 Extra keys (all optional, the reference's single key keeps working):
   dtype         'complex64' (default) | 'complex128'
-  screen_method 'exact' | 'tc'            float64 CUDA-core contraction | tcgen05 tensor-core contraction
+  screen_method 'auto' | 'exact' | 'tc'   float64 CUDA-core contraction | tcgen05 split-fp16 tensor-core contraction;
+                'auto' = 'tc' for complex64 grids whose size is a multiple of 256, else 'exact'
   theta_cut     phase-argument bound (rad) below which rings are summed as a float64 polynomial
+                (None = 10 for the tensor-core method, 2 for the exact one)
   rng           'numpy' (reference draw order from numpy's global RNG; parity mode) | 'philox' (device RNG)
   seed          seed of the device RNG
   batch         realizations per launch in Simulation's batched fast path
@@ -20,8 +22,8 @@ import numpy as np
 config = {
     "use_gpu": True,
     "dtype": "complex64",
-    "screen_method": "exact",
-    "theta_cut": 2.0,
+    "screen_method": "auto",
+    "theta_cut": None,
     "rng": "numpy",
     "seed": 0,
     "batch": 8,

@@ -92,7 +92,7 @@ class PhaseScreensPath(AbstractPath):
             degree = -1
         return eng.PathDescriptor(legs, scales, final, src.wvl, getattr(src, "w0", 1.0), getattr(src, "F0", np.inf),
                                   ps.f_grid.points, m_split, degree, shift,
-                                  eng.SCREEN_METHODS[gpu.config["screen_method"]], from_field,
+                                  eng.screen_method(self.channel.grid.resolution[0]), from_field,
                                   coef_bound=max(eng.coef_bound(q._get_psd(), m_split) for q in self.phase_screens))
 
     def _draw_spectra(self, wind):

@@ -98,7 +98,8 @@ class SSPhaseScreen(PhaseScreen):
         x, y = self.grid.get_xy()
         xe = float(np.max(np.abs(x + np.float32(shift[0]))))
         ye = float(np.max(np.abs(y + np.float32(shift[1]))))
-        return eng.plan_low_rings(self.f_grid.base, self._get_psd(), xe, ye, gpu.config["theta_cut"], eng.screen_tolerance())
+        return eng.plan_low_rings(self.f_grid.base, self._get_psd(), xe, ye, eng.theta_cut(self.grid.resolution[0]),
+                                  eng.screen_tolerance())
 
     def _synthesize(self, spectrum, shift, want_turns=True, want_phi=False, imag_part=False):
         """Run pa_screen_ss for one spectrum.  Returns (turns, phi) torch tensors (None when not requested)."""
@@ -120,7 +121,7 @@ class SSPhaseScreen(PhaseScreen):
         nat.check(ctx.lib.pa_screen_ss(ctx.handle, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(c_d), m, m_split, degree,
                                        float(shift[0]), float(shift[1]), 1, nat.ptr(turns), nat.ptr(phi),
                                        1 if ctx.precision == nat.PA_C128 else 0,
-                                       eng.SCREEN_METHODS[gpu.config["screen_method"]],
+                                       eng.screen_method(n),
                                        float(np.max(np.abs(coef[m_split:]))) if m_split < m else 1.0, nat.stream_ptr()))
         return turns, phi
 

@@ -3,6 +3,7 @@ fixtures produced by the reference.  Run on the B200 box: python -m pytest tests
 
 Stated tolerances (relative L2 of the complex field unless noted):
   complex64  path vs float64 oracle : 1e-5       complex128 path vs float64 oracle : 1e-10
+  (complex64 with the tensor-core screen synthesis: see tests/test_gpu_screen_tc.py)
   any path vs the reference's own complex64 output: 5e-3 on turbulent fields -- the reference's complex64
   screens are themselves ~3e-4 rad away from their float64 evaluation, a floor we do not copy.
 """
@@ -28,7 +29,10 @@ def _cfg():
 
 
 def _pa(dtype="complex64", **kw):
+    """Tests in this file pin the float64 CUDA-core screen path unless they ask for the tensor-core one."""
     import pyatmosphere_b200 as pa
+    kw.setdefault("screen_method", "exact")
+    kw.setdefault("theta_cut", 2.0)
     pa.gpu.config.update(use_gpu=True, dtype=dtype, **kw)
     return pa
 

@@ -48,6 +48,16 @@ def run(n, theta_cut, nscreens=1):
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
         out[method] = (phi.cpu().numpy(), turns.cpu().numpy(), dt)
+    # production configuration: turns only (no full-phase output), CUDA-event timing
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    ev0.record()
+    for _ in range(reps):
+        nat.check(ctx.lib.pa_screen_ss(ctx.handle, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), m, m_split, degree, 0.0, 0.0,
+                                       nscreens, nat.ptr(turns), None, 0, 1, bound, nat.stream_ptr()))
+    ev1.record()
+    torch.cuda.synchronize()
+    print(f"   tc turns-only: {ev0.elapsed_time(ev1) / reps * 1e3 / nscreens:.1f} us per screen (all kernels)")
     e = out[1][0] - out[0][0]
     et = np.abs(np.exp(-2j * np.pi * out[1][1].astype(np.float64)) - np.exp(-2j * np.pi * out[0][1].astype(np.float64)))
     print(f"n={n} theta_cut={theta_cut} m_split={m_split} degree={degree} bound={bound:.2f} nscreens={nscreens}: "
