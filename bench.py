@@ -207,12 +207,19 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step_device(i)
-    barrier()
+    # the clock sampler is started BEFORE the warm-up and given time to come up: nvidia-smi's own start-up stalls
+    # kernel launches for tens of milliseconds and must not land inside the timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 5.0:
+            time.sleep(0.05)
+    for i in range(args.warmup):
+        step_device(i)
+    barrier()
+    if rank == 0:
+        sampler.rows.clear()
     nat.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -359,7 +366,7 @@ def main():
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
     else:
-        args.steps = args.steps if args.steps is not None else 10
+        args.steps = args.steps if args.steps is not None else 40
         args.warmup = max(3, args.warmup if args.warmup is not None else 3)
         run_gpu(args)
 
