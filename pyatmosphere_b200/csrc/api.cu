@@ -2,6 +2,7 @@
 // split-step passes.  Host code only; kernels live in fft_n*.cu, screen*.cu, measure.cu, rng.cu.
 #include "../../include/pyatm_b200.h"
 
+#include <cuda.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
@@ -32,6 +33,17 @@ const char* last_error() { return g_err; }
 static std::atomic<unsigned long long> g_launches{0};
 static inline void note(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+struct TensorMapEntry {
+    const void* field;
+    int batch;
+    CUtensorMap map;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
 struct HTable {
     double length, wvl;
     void* dev;            // cplx<T>[n] permuted transfer-function factor
@@ -61,6 +73,8 @@ struct pa_ctx {
     float* spec = nullptr; size_t spec_bytes = 0;        // fx | fy | coef staging for pa_simulate_batch
     float* pupils = nullptr; size_t pupils_bytes = 0;
     double* table = nullptr; size_t table_bytes = 0;
+    std::vector<TensorMapEntry> tmaps;   // column-pass tensor maps, keyed by (field pointer, batch)
+    bool use_tma = true;
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
     int num_sms = 148;
@@ -107,18 +121,26 @@ template <typename T> static int build_twiddles(pa_ctx* c) {
     return PA_OK;
 }
 
+// perm[q] = frequency (numpy fft index) stored at index q of a spectrum.  Register idx of thread t holds, after
+// the last forward stage, position p = base_{L-1}(t, g) + j (idx = g R + j), whose frequency is the mixed-radix
+// digit reversal of p; it is stored at q = t + idx * (n/e)  (fft_core.cuh: io_pos).
 static void build_perm(pa_ctx* c) {
-    const int n = c->n, e = c->e, L = plan_len(n, e);
-    c->perm.resize(n);
-    for (int p = 0; p < n; ++p) {
-        int k = 0, mult = 1;
-        for (int s = 0; s < L; ++s) {
-            const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s);
-            k += ((p / sigma) % R) * mult;
-            mult *= R;
+    const int n = c->n, e = c->e, L = plan_len(n, e), tpf = n / e;
+    const int RL = plan_radix(n, e, L - 1), SL = plan_sigma(n, e, L - 1);
+    c->perm.assign(n, -1);
+    for (int t = 0; t < tpf; ++t)
+        for (int idx = 0; idx < e; ++idx) {
+            const int g = idx / RL, j = idx % RL;
+            const int b = t + g * tpf;
+            const int p = (b / SL) * (SL * RL) + (b % SL) + j * SL;
+            int k = 0, mult = 1;
+            for (int s = 0; s < L; ++s) {
+                const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s);
+                k += ((p / sigma) % R) * mult;
+                mult *= R;
+            }
+            c->perm[t + idx * tpf] = k;
         }
-        c->perm[p] = k;
-    }
 }
 
 // Transfer function of one leg, separable and in permuted order:
@@ -167,6 +189,41 @@ static int get_htable(pa_ctx* c, double length, double wvl, const HTable** out) 
     return PA_OK;
 }
 
+// 2-D tensor map of a field for the column pass: [batch*n rows][2n reals], box = (2*TC reals) x (256 rows).
+static int get_tensor_map(pa_ctx* c, void* field, int batch, const CUtensorMap** out) {
+    for (const auto& e : c->tmaps)
+        if (e.field == field && e.batch == batch) {
+            *out = &e.map;
+            return PA_OK;
+        }
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        PA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        PA_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        g_encode = (EncodeTiledFn)fn;
+    }
+    const int n = c->n;
+    const size_t csz = c->csize();
+    const int tc = 65536 / (n * (int)csz);
+    const int boxr = n < 256 ? n : 256;
+    TensorMapEntry e;
+    e.field = field;
+    e.batch = batch;
+    const cuuint64_t dims[2] = {(cuuint64_t)2 * n, (cuuint64_t)batch * n};
+    const cuuint64_t strides[1] = {(cuuint64_t)n * csz};
+    const cuuint32_t box[2] = {(cuuint32_t)(2 * tc), (cuuint32_t)boxr};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(&e.map, c->prec == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, field, dims,
+                                strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    PA_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    if (c->tmaps.size() >= 64) c->tmaps.erase(c->tmaps.begin());
+    c->tmaps.push_back(e);
+    *out = &c->tmaps.back().map;
+    return PA_OK;
+}
+
 // ---- pass helpers -----------------------------------------------------------------------------------------
 static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, bool src, const void* turns, double scale,
                 double amp, double aw, double ac, cudaStream_t st) {
@@ -184,6 +241,8 @@ static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, 
     r.amp = amp;
     r.aw = aw;
     r.ac = ac;
+    r.use_tma = c->use_tma;
+    r.num_sms = c->num_sms;
     note(1);
     return check_launch(launch_rows(c->prec, c->n, r, st), "row pass");
 }
@@ -198,6 +257,14 @@ static int cols(pa_ctx* c, void* field, int batch, double length, double wvl, cu
     cl.alpha_re = h->alpha_re;
     cl.alpha_im = h->alpha_im;
     cl.batch = batch;
+    cl.tmap = nullptr;
+    cl.num_sms = c->num_sms;
+    if (c->use_tma && fft_tma_supported(c->prec, c->n)) {
+        const CUtensorMap* tm = nullptr;
+        rc = get_tensor_map(c, field, batch, &tm);
+        if (rc) return rc;
+        cl.tmap = tm;
+    }
     note(1);
     return check_launch(launch_cols(c->prec, c->n, cl, st), "column pass");
 }
@@ -338,6 +405,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     }
     c->htabs.reserve(256);
     c->num_sms = prop.multiProcessorCount;
+    c->use_tma = !(getenv("PYATM_FFT_DIRECT") && atoi(getenv("PYATM_FFT_DIRECT")) != 0);
     *out = c;
     return PA_OK;
 }

@@ -6,7 +6,7 @@
 // frequency k = sum_s d_s * prod_{u<s} R_u at position p = sum_s d_s * SIGMA_s (mixed-radix digit
 // reversal).  The inverse runs the same stages backwards (conjugate twiddle, then inverse butterfly) and so
 // maps the permuted spectrum back to natural order.  The permuted order is never undone on the device: the
-// split-step path only multiplies spectra element-wise, by tables that the host stores in permuted order.
+// split-step path only multiplies spectra element-wise, by tables that the host stores in the same order.
 //
 // Each thread owns E elements; a transform uses N/E threads.  At stage s a thread owns G = E/R butterflies;
 // butterfly b = t + g*(N/E) touches positions base(b) + j*SIGMA, base(b) = (b/SIGMA)*SIGMA*R + b%SIGMA.
@@ -188,6 +188,12 @@ template <typename T, int N, int E, int S> __device__ __forceinline__ void stage
     }
     dft_groups<T, St::R, true, St::G, E>(v);
 }
+
+// STORAGE ORDER of a spectrum: the register idx of thread t after the last forward stage (which holds position
+// reg_pos<L-1>(t, idx)) is stored at index  t + idx * (N/E).  All global / TMA-staged I/O is therefore a unit-
+// stride access over the threads of a transform, for natural data (reg_pos<0> has the same form) and for
+// spectra alike; the resulting permutation (storage index -> frequency) is exported by pa_ctx_permutation.
+template <int N, int E> __device__ __forceinline__ int io_pos(int t, int idx) { return t + idx * (N / E); }
 
 // position of register idx of thread t in the distribution of stage S
 template <int N, int E, int S> __device__ __forceinline__ int reg_pos(int t, int idx) {

@@ -27,6 +27,14 @@ bool fft_size_supported(int prec, int n) {
         default: return false;
     }
 }
+bool fft_tma_supported(int prec, int n) {
+    switch (n) {
+#define PA_CASE(N) case N: return fft_tma_ok_##N(prec);
+        PA_FFT_SIZES(PA_CASE)
+#undef PA_CASE
+        default: return false;
+    }
+}
 void fft_geometry(int prec, int n, int* rt, int* rf, int* rs, int* ct, int* cc, int* cs) {
     int g[6] = {0, 0, 0, 0, 0, 0};
     switch (n) {

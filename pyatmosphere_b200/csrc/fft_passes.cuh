@@ -68,7 +68,6 @@ template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool S
 __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
     using C = cplx<T>;
     constexpr int TPF = N / E;
-    constexpr int L = plan_len(N, E);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* sm = reinterpret_cast<C*>(smem_raw);
     const int f = threadIdx.x / TPF;
@@ -96,22 +95,8 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
             }
         }
     } else if constexpr (IN_PERM) {
-        using St = Stage<N, E, L - 1>;      // SIGMA == 1: runs of R consecutive positions
 #pragma unroll
-        for (int g = 0; g < St::G; ++g) {
-            const C* src = ptr + St::base(t, g);
-            if constexpr (sizeof(C) == 8 && St::R % 2 == 0) {
-#pragma unroll
-                for (int j = 0; j < St::R; j += 2) {
-                    const float4 q = *reinterpret_cast<const float4*>(src + j);
-                    v[g * St::R + j] = mkc<T>(q.x, q.y);
-                    v[g * St::R + j + 1] = mkc<T>(q.z, q.w);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < St::R; ++j) v[g * St::R + j] = src[j];
-            }
-        }
+        for (int i = 0; i < E; ++i) v[i] = ptr[io_pos<N, E>(t, i)];      // spectrum in storage order
         fft_inv<T, N, E>(v, t, sm, addr, a.tw);
     } else {
 #pragma unroll
@@ -138,20 +123,8 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
 
     if constexpr (OUT_PERM) {
         fft_fwd<T, N, E>(v, t, sm, addr, a.tw);
-        using St = Stage<N, E, L - 1>;
 #pragma unroll
-        for (int g = 0; g < St::G; ++g) {
-            C* dst = ptr + St::base(t, g);
-            if constexpr (sizeof(C) == 8 && St::R % 2 == 0) {
-#pragma unroll
-                for (int j = 0; j < St::R; j += 2)
-                    *reinterpret_cast<float4*>(dst + j) =
-                        make_float4(v[g * St::R + j].x, v[g * St::R + j].y, v[g * St::R + j + 1].x, v[g * St::R + j + 1].y);
-            } else {
-#pragma unroll
-                for (int j = 0; j < St::R; ++j) dst[j] = v[g * St::R + j];
-            }
-        }
+        for (int i = 0; i < E; ++i) ptr[io_pos<N, E>(t, i)] = v[i];
     } else {
 #pragma unroll
         for (int i = 0; i < E; ++i) ptr[reg_pos<N, E, 0>(t, i)] = v[i];
@@ -161,7 +134,7 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
 template <typename T> struct ColArgs {
     cplx<T>* field;        // [batch][N][N] in place, row-spectrum form
     const cplx<T>* tw;
-    const cplx<T>* hp;     // transfer-function factor h[freq(p)] in permuted order, N entries
+    const cplx<T>* hp;     // transfer-function factor h[freq(q)] in spectrum storage order, N entries
     T alpha_re, alpha_im;  // e^{ikL} / N^2 (times any loss factor)
 };
 
@@ -188,7 +161,7 @@ __global__ void __launch_bounds__(TC * (N / E)) k_cols(ColArgs<T> a) {
         const C hx = cmul(ldg_c<T>(a.hp + col), mkc<T>(a.alpha_re, a.alpha_im));
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-            const C h = cmul(ldg_c<T>(a.hp + reg_pos<N, E, L - 1>(t, i)), hx);
+            const C h = cmul(ldg_c<T>(a.hp + io_pos<N, E>(t, i)), hx);     // register (t,i) holds storage index t + i*T
             v[i] = cmul(v[i], h);
         }
     }

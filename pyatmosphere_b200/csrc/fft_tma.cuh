@@ -1,0 +1,182 @@
+// TMA-fed persistent variants of the two FFT passes.
+//
+// One CTA per SM loops over tiles (FPB rows, or TC adjacent columns, = 64 KiB of field).  Tiles travel through a
+// ring of three shared-memory slots: while the 512 compute threads transform the tile in slot k%3 (the exchanges
+// of the register FFT run inside that same slot), the TMA engine loads tile k+1 / k+2 into the other slots and
+// drains the result of tile k-1 back to HBM.  The compute threads never issue a global load or store for the
+// field, so the `lg_throttle` / `long_scoreboard` stalls of the direct-access kernels (profiles/r1_prof_*.txt)
+// are gone and loads, math and stores overlap.
+//
+//   rows   : tiles are contiguous in memory -> 1-D bulk copies (cp.async.bulk), no tensor map
+//   columns: TC columns x N rows -> 2-D tiled tensor copies (cp.async.bulk.tensor.2d), boxes of 256 rows
+//
+// Data is staged in plain linear order; thanks to the unit-stride storage order (fft_core.cuh: io_pos) the
+// register <-> slot moves at both ends are bank-conflict-free without any hardware swizzle.
+#pragma once
+#include <cuda.h>
+
+#include "async_ptx.cuh"
+#include "fft_passes.cuh"
+
+namespace pa {
+
+constexpr int kSlots = 3;
+constexpr int kSlotBytes = 65536;
+
+template <typename T, int N, int E> struct TmaGeo {
+    using C = cplx<T>;
+    static constexpr int TPF = N / E;
+    static constexpr int FPB = kSlotBytes / (N * (int)sizeof(C));          // rows per tile
+    static constexpr int TC = kSlotBytes / (N * (int)sizeof(C));           // columns per tile
+    static constexpr int THREADS = FPB * TPF;
+    static constexpr int BOXR = N < 256 ? N : 256;                          // rows per tensor box
+    static constexpr int SMEM = kSlots * kSlotBytes + 64;
+    static constexpr bool OK = FPB >= 1 && THREADS <= 1024 && THREADS >= 64 && TC * (int)sizeof(C) >= 16 && TC <= 32;
+};
+
+template <typename T, int N, int E, bool IN_PERM, bool OUT_PERM>
+__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_rows_tma(RowArgs<T> a, int ntiles) {
+    using C = cplx<T>;
+    using G = TmaGeo<T, N, E>;
+    constexpr int TPF = G::TPF, FPB = G::FPB;
+    extern __shared__ __align__(1024) unsigned char smem_tma[];
+    C* slots = reinterpret_cast<C*>(smem_tma);
+    const uint32_t slot0 = ptx::smem_u32(smem_tma);
+    const uint32_t bar0 = slot0 + kSlots * kSlotBytes;
+    const int f = threadIdx.x / TPF, t = threadIdx.x % TPF;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue_load = [&](int k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= ntiles) return;
+        const int slot = k % kSlots;
+        ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
+        const char* src = reinterpret_cast<const char*>(a.field) + (size_t)tile * kSlotBytes;
+#pragma unroll
+        for (int o = 0; o < kSlotBytes; o += 16384) ptx::bulk_g2s(slot0 + slot * kSlotBytes + o, src + o, 16384, bar0 + 8 * slot);
+        if (a.turns != nullptr)      // pull the tile's screen rows towards L2 ahead of the compute threads
+            ptx::bulk_prefetch_l2(reinterpret_cast<const char*>(a.turns) + (size_t)tile * (kSlotBytes / 2), kSlotBytes / 2);
+    };
+    if (threadIdx.x == 0) {
+        issue_load(0);
+        issue_load(1);
+    }
+    const RowAddr<N, E> addr{f * N};
+    for (int k = 0;; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= ntiles) break;
+        const int slot = k % kSlots;
+        C* sm = slots + (size_t)slot * (kSlotBytes / sizeof(C));
+        const int row = tile * FPB + f;
+        ptx::mbar_wait(bar0 + 8 * slot, (k / kSlots) & 1);
+        C v[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = sm[f * N + (IN_PERM ? io_pos<N, E>(t, i) : reg_pos<N, E, 0>(t, i))];
+        __syncthreads();                                   // slot is now scratch for the exchanges
+        if constexpr (IN_PERM) fft_inv<T, N, E>(v, t, sm, addr, a.tw);
+        if (a.turns != nullptr) {
+            const T* tr = a.turns + (size_t)row * N;
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                C e = expm2pi(tr[reg_pos<N, E, 0>(t, i)]);
+                e.x *= a.scale;
+                e.y *= a.scale;
+                v[i] = cmul(v[i], e);
+            }
+        } else if (a.scale != (T)1) {
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                v[i].x *= a.scale;
+                v[i].y *= a.scale;
+            }
+        }
+        if constexpr (OUT_PERM) fft_fwd<T, N, E>(v, t, sm, addr, a.tw);
+        __syncthreads();                                   // every exchange read is done
+#pragma unroll
+        for (int i = 0; i < E; ++i) sm[f * N + (OUT_PERM ? io_pos<N, E>(t, i) : reg_pos<N, E, 0>(t, i))] = v[i];
+        ptx::fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ptx::bulk_s2g(reinterpret_cast<char*>(a.field) + (size_t)tile * kSlotBytes, slot0 + slot * kSlotBytes, kSlotBytes);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<1>();                      // the store of tile k-1 has left its slot ...
+            issue_load(k + 2);                             // ... which is the slot of tile k+2
+        }
+    }
+    if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
+}
+
+template <typename T, int N, int E>
+__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
+    using C = cplx<T>;
+    using G = TmaGeo<T, N, E>;
+    constexpr int TC = G::TC, BOXR = G::BOXR;
+    constexpr int TILES_PER_FIELD = N / TC;
+    constexpr int BOX_BYTES = BOXR * TC * (int)sizeof(C);
+    extern __shared__ __align__(1024) unsigned char smem_tma[];
+    C* slots = reinterpret_cast<C*>(smem_tma);
+    const uint32_t slot0 = ptx::smem_u32(smem_tma);
+    const uint32_t bar0 = slot0 + kSlots * kSlotBytes;
+    const int c = threadIdx.x % TC, t = threadIdx.x / TC;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue_load = [&](int k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= ntiles) return;
+        const int slot = k % kSlots;
+        const int b = tile / TILES_PER_FIELD, col0 = (tile % TILES_PER_FIELD) * TC;
+        ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
+#pragma unroll
+        for (int r = 0; r < N / BOXR; ++r)
+            ptx::tma_load_2d(slot0 + slot * kSlotBytes + r * BOX_BYTES, &tmap, col0 * 2, b * N + r * BOXR, bar0 + 8 * slot);
+    };
+    if (threadIdx.x == 0) {
+        issue_load(0);
+        issue_load(1);
+    }
+    const ColAddr<N, E, TC> addr{c};
+    for (int k = 0;; ++k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (tile >= ntiles) break;
+        const int slot = k % kSlots;
+        C* sm = slots + (size_t)slot * (kSlotBytes / sizeof(C));
+        const int col = (tile % TILES_PER_FIELD) * TC + c;
+        ptx::mbar_wait(bar0 + 8 * slot, (k / kSlots) & 1);
+        C v[E];
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = sm[reg_pos<N, E, 0>(t, i) * TC + c];
+        __syncthreads();
+        fft_fwd<T, N, E>(v, t, sm, addr, a.tw);
+        {
+            const C hx = cmul(ldg_c<T>(a.hp + col), mkc<T>(a.alpha_re, a.alpha_im));
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const C h = cmul(ldg_c<T>(a.hp + io_pos<N, E>(t, i)), hx);
+                v[i] = cmul(v[i], h);
+            }
+        }
+        fft_inv<T, N, E>(v, t, sm, addr, a.tw);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < E; ++i) sm[reg_pos<N, E, 0>(t, i) * TC + c] = v[i];
+        ptx::fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int b = tile / TILES_PER_FIELD, col0 = (tile % TILES_PER_FIELD) * TC;
+#pragma unroll
+            for (int r = 0; r < N / BOXR; ++r) ptx::tma_store_2d(&tmap, col0 * 2, b * N + r * BOXR, slot0 + slot * kSlotBytes + r * BOX_BYTES);
+            ptx::bulk_commit();
+            ptx::bulk_wait_read<1>();
+            issue_load(k + 2);
+        }
+    }
+    if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
+}
+
+}  // namespace pa

@@ -23,6 +23,8 @@ struct RowLaunch {
     const float* x;
     const float* y;
     double amp, aw, ac;
+    bool use_tma;         // persistent TMA-fed variant (ignored where it does not exist)
+    int num_sms;
 };
 struct ColLaunch {
     void* field;          // cplx<T>* [batch][n][n]
@@ -30,12 +32,15 @@ struct ColLaunch {
     const void* hp;       // cplx<T>* permuted transfer-function factor
     double alpha_re, alpha_im;
     int batch;
+    const void* tmap;     // host pointer to a CUtensorMap of the field ([batch*n][2n] reals), or null -> direct-access kernel
+    int num_sms;
 };
 
 // implemented once per grid size in fft_n<N>.cu; return cudaError_t as int, or -1 for an unsupported size
 int launch_rows(int prec, int n, const RowLaunch& a, cudaStream_t st);
 int launch_cols(int prec, int n, const ColLaunch& a, cudaStream_t st);
 bool fft_size_supported(int prec, int n);
+bool fft_tma_supported(int prec, int n);
 // number of CTAs / threads / smem of the two passes (reported through pa_fft_geometry for the roofline notes)
 void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_smem, int* cols_threads, int* cols_tc, int* cols_smem);
 
@@ -43,7 +48,8 @@ void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_s
 #define PA_DECL(N)                                                                   \
     int launch_rows_##N(int prec, const RowLaunch& a, cudaStream_t st);              \
     int launch_cols_##N(int prec, const ColLaunch& a, cudaStream_t st);              \
-    void fft_geometry_##N(int prec, int* g);
+    void fft_geometry_##N(int prec, int* g);                                         \
+    bool fft_tma_ok_##N(int prec);
 PA_FFT_SIZES(PA_DECL)
 #undef PA_DECL
 
