@@ -118,44 +118,55 @@ def run_reference(args):
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and throttle reasons of one GPU during the timed region.  In-process NVML (nvidia_ml_py)
+    every 200 ms (clock + event reasons only).  Polling is deliberately sparse: on these hosts every NVML /
+    nvidia-smi poll stalls the GPU for milliseconds (50 ms polling cost 30 % of the throughput)."""
 
     def __init__(self, device):
-        self.device, self.rows, self.proc = device, [], None
+        self.device, self.rows, self.thread, self.stop_flag = device, [], None, False
+        self.err = None
+        self.period = 0.2       # NVML polling itself perturbs the GPU (measured: -30% at 50 ms); keep it sparse
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.device)
+            self.max_sm = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:          # noqa: BLE001
+            self.err = repr(e)
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:       # noqa: BLE001  (older binding name)
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((sm, reasons, time.perf_counter()))
+            except Exception as e:      # noqa: BLE001
+                self.err = repr(e)
+                return
+            time.sleep(self.period)
+
+    def stop(self, t0=None, t1=None):
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=2)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: " + str(self.err)]}
+        nv = self.nv
+        busy = [r for r in self.rows if t0 is not None and t0 <= r[2] <= t1] or self.rows[-3:]
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in busy))
+        return {"sm_mhz": statistics.median(r[0] for r in busy), "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(busy)}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -212,9 +223,7 @@ def run_gpu(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        t_wait = time.time()
-        while not sampler.rows and time.time() - t_wait < 5.0:
-            time.sleep(0.05)
+        time.sleep(0.2)
     for i in range(args.warmup):
         step_device(i)
     barrier()
@@ -223,6 +232,7 @@ def run_gpu(args):
     nat.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    t_begin = time.perf_counter()
     e0.record()
     for i in range(args.steps):
         step_device(args.warmup + i)
@@ -245,7 +255,7 @@ def run_gpu(args):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     value = world * args.steps * B / (ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------

@@ -74,7 +74,8 @@ struct pa_ctx {
     float* pupils = nullptr; size_t pupils_bytes = 0;
     double* table = nullptr; size_t table_bytes = 0;
     std::vector<TensorMapEntry> tmaps;   // column-pass tensor maps, keyed by (field pointer, batch)
-    bool use_tma = true;
+    bool use_tma = true;        // column pass: TMA-fed persistent kernel
+    bool rows_tma = false;      // row pass: the direct-access kernel is faster (smem-bound), TMA variant kept for experiments
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
     int num_sms = 148;
@@ -205,7 +206,7 @@ static int get_tensor_map(pa_ctx* c, void* field, int batch, const CUtensorMap**
     }
     const int n = c->n;
     const size_t csz = c->csize();
-    const int tc = 65536 / (n * (int)csz);
+    const int tc = fft_tma_cols_per_tile(c->prec, n);
     const int boxr = n < 256 ? n : 256;
     TensorMapEntry e;
     e.field = field;
@@ -241,7 +242,7 @@ static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, 
     r.amp = amp;
     r.aw = aw;
     r.ac = ac;
-    r.use_tma = c->use_tma;
+    r.use_tma = c->rows_tma;
     r.num_sms = c->num_sms;
     note(1);
     return check_launch(launch_rows(c->prec, c->n, r, st), "row pass");
@@ -406,6 +407,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     c->htabs.reserve(256);
     c->num_sms = prop.multiProcessorCount;
     c->use_tma = !(getenv("PYATM_FFT_DIRECT") && atoi(getenv("PYATM_FFT_DIRECT")) != 0);
+    c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") && atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0;
     *out = c;
     return PA_OK;
 }

@@ -35,6 +35,14 @@ bool fft_tma_supported(int prec, int n) {
         default: return false;
     }
 }
+int fft_tma_cols_per_tile(int prec, int n) {
+    switch (n) {
+#define PA_CASE(N) case N: return fft_tma_tc_##N(prec);
+        PA_FFT_SIZES(PA_CASE)
+#undef PA_CASE
+        default: return 0;
+    }
+}
 void fft_geometry(int prec, int n, int* rt, int* rf, int* rs, int* ct, int* cc, int* cs) {
     int g[6] = {0, 0, 0, 0, 0, 0};
     switch (n) {

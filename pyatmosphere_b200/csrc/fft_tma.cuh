@@ -21,24 +21,43 @@
 namespace pa {
 
 constexpr int kSlots = 3;
-constexpr int kSlotBytes = 65536;
+#ifndef PA_TMA_ROW_THREADS
+#define PA_TMA_ROW_THREADS 128      // row pass: small CTAs (one 2048-point row each), several per SM
+#endif
+#ifndef PA_TMA_COL_BYTES
+#define PA_TMA_COL_BYTES 65536      // column pass: 64 KiB tiles (4 columns of 2048 complex64)
+#endif
 
+// geometry of the row pass: FPB rows per tile so that a CTA has about PA_TMA_ROW_THREADS threads
+template <typename T, int N, int E> struct TmaRowGeo {
+    using C = cplx<T>;
+    static constexpr int TPF = N / E;
+    static constexpr int FPB = (PA_TMA_ROW_THREADS / TPF) > 0 ? (PA_TMA_ROW_THREADS / TPF) : 1;
+    static constexpr int THREADS = FPB * TPF;
+    static constexpr int SLOT = FPB * N * (int)sizeof(C);
+    static constexpr int CHUNK = SLOT < 16384 ? SLOT : 16384;               // bytes per bulk copy
+    static constexpr int SMEM = kSlots * SLOT + 64;
+    static constexpr bool OK = THREADS <= 1024 && THREADS >= 32 && SMEM <= 227 * 1024 && SLOT % 16 == 0;
+};
+// geometry of the column pass: TC adjacent columns per tile
 template <typename T, int N, int E> struct TmaGeo {
     using C = cplx<T>;
     static constexpr int TPF = N / E;
-    static constexpr int FPB = kSlotBytes / (N * (int)sizeof(C));          // rows per tile
-    static constexpr int TC = kSlotBytes / (N * (int)sizeof(C));           // columns per tile
-    static constexpr int THREADS = FPB * TPF;
+    static constexpr int TC = PA_TMA_COL_BYTES / (N * (int)sizeof(C));
+    static constexpr int THREADS = TC * TPF;
+    static constexpr int SLOT = TC * N * (int)sizeof(C);
     static constexpr int BOXR = N < 256 ? N : 256;                          // rows per tensor box
-    static constexpr int SMEM = kSlots * kSlotBytes + 64;
-    static constexpr bool OK = FPB >= 1 && THREADS <= 1024 && THREADS >= 64 && TC * (int)sizeof(C) >= 16 && TC <= 32;
+    static constexpr int SMEM = kSlots * SLOT + 64;
+    static constexpr bool OK = TC >= 1 && THREADS <= 1024 && THREADS >= 64 && TC * (int)sizeof(C) >= 16 && TC <= 32 &&
+                               TmaRowGeo<T, N, E>::OK;
 };
 
 template <typename T, int N, int E, bool IN_PERM, bool OUT_PERM>
-__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_rows_tma(RowArgs<T> a, int ntiles) {
+__global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArgs<T> a, int ntiles) {
     using C = cplx<T>;
-    using G = TmaGeo<T, N, E>;
+    using G = TmaRowGeo<T, N, E>;
     constexpr int TPF = G::TPF, FPB = G::FPB;
+    constexpr int kSlotBytes = G::SLOT;
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     C* slots = reinterpret_cast<C*>(smem_tma);
     const uint32_t slot0 = ptx::smem_u32(smem_tma);
@@ -56,7 +75,7 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_rows_tma(RowArg
         ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
         const char* src = reinterpret_cast<const char*>(a.field) + (size_t)tile * kSlotBytes;
 #pragma unroll
-        for (int o = 0; o < kSlotBytes; o += 16384) ptx::bulk_g2s(slot0 + slot * kSlotBytes + o, src + o, 16384, bar0 + 8 * slot);
+        for (int o = 0; o < kSlotBytes; o += G::CHUNK) ptx::bulk_g2s(slot0 + slot * kSlotBytes + o, src + o, G::CHUNK, bar0 + 8 * slot);
         if (a.turns != nullptr)      // pull the tile's screen rows towards L2 ahead of the compute threads
             ptx::bulk_prefetch_l2(reinterpret_cast<const char*>(a.turns) + (size_t)tile * (kSlotBytes / 2), kSlotBytes / 2);
     };
@@ -114,6 +133,7 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
     using C = cplx<T>;
     using G = TmaGeo<T, N, E>;
     constexpr int TC = G::TC, BOXR = G::BOXR;
+    constexpr int kSlotBytes = G::SLOT;
     constexpr int TILES_PER_FIELD = N / TC;
     constexpr int BOX_BYTES = BOXR * TC * (int)sizeof(C);
     extern __shared__ __align__(1024) unsigned char smem_tma[];

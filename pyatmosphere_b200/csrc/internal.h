@@ -41,6 +41,7 @@ int launch_rows(int prec, int n, const RowLaunch& a, cudaStream_t st);
 int launch_cols(int prec, int n, const ColLaunch& a, cudaStream_t st);
 bool fft_size_supported(int prec, int n);
 bool fft_tma_supported(int prec, int n);
+int fft_tma_cols_per_tile(int prec, int n);
 // number of CTAs / threads / smem of the two passes (reported through pa_fft_geometry for the roofline notes)
 void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_smem, int* cols_threads, int* cols_tc, int* cols_smem);
 
@@ -49,7 +50,8 @@ void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_s
     int launch_rows_##N(int prec, const RowLaunch& a, cudaStream_t st);              \
     int launch_cols_##N(int prec, const ColLaunch& a, cudaStream_t st);              \
     void fft_geometry_##N(int prec, int* g);                                         \
-    bool fft_tma_ok_##N(int prec);
+    bool fft_tma_ok_##N(int prec);                                                   \
+    int fft_tma_tc_##N(int prec);
 PA_FFT_SIZES(PA_DECL)
 #undef PA_DECL
 
