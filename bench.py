@@ -217,15 +217,31 @@ def run_gpu(args):
             td.barrier()
         torch.cuda.synchronize()
 
+    edges = torch.linspace(0, 1, 201, dtype=torch.float64, device=dev)
+
+    def reduce_stats(lo, hi):
+        """The only collective of the path: PDT histogram + beam-statistics sums of the realizations of steps
+        [lo, hi), all-reduced over the ranks (NCCL)."""
+        tab = table_d[lo:hi].reshape(-1, stride)
+        hist = torch.zeros(200, dtype=torch.int64, device=dev)
+        nat.check(lib.pa_histogram(h, nat.ptr(tab[:, nat.MEASURE_HEAD:]), stride, tab.shape[0], nat.ptr(edges), 200, nat.ptr(hist), stream))
+        sums = torch.stack([tab[:, 1].pow(2).sum(), tab[:, 1].pow(4).sum(), tab[:, 3].sum(), tab[:, 3].pow(2).sum()])
+        if world > 1:
+            import torch.distributed as td
+            td.all_reduce(hist)
+            td.all_reduce(sums)
+        return hist, sums, tab
+
     # ---- device-resident throughput ------------------------------------------------------------------------
     # the clock sampler is started BEFORE the warm-up and given time to come up: nvidia-smi's own start-up stalls
     # kernel launches for tens of milliseconds and must not land inside the timed region
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("PYATM_BENCH_NOSAMPLER"):
         sampler.start()
         time.sleep(0.2)
     for i in range(args.warmup):
         step_device(i)
+    reduce_stats(0, args.warmup)          # also warms up the lazily loaded torch / NCCL kernels of the reduction
     barrier()
     if rank == 0:
         sampler.rows.clear()
@@ -234,21 +250,20 @@ def run_gpu(args):
     barrier()
     t_begin = time.perf_counter()
     e0.record()
+    step_events = []
     for i in range(args.steps):
         step_device(args.warmup + i)
-    # the only collective of the path: PDT histogram + beam statistics of everything computed so far
-    tab = table_d[args.warmup:].reshape(-1, stride)
-    edges = torch.linspace(0, 1, 201, dtype=torch.float64, device=dev)
-    hist = torch.zeros(200, dtype=torch.int64, device=dev)
-    nat.check(lib.pa_histogram(h, nat.ptr(tab[:, nat.MEASURE_HEAD:]), stride, tab.shape[0], nat.ptr(edges), 200, nat.ptr(hist), stream))
-    sums = torch.stack([tab[:, 1].pow(2).sum(), tab[:, 1].pow(4).sum(), tab[:, 3].sum(), tab[:, 3].pow(2).sum()])
-    if world > 1:
-        import torch.distributed as td
-        td.all_reduce(hist)
-        td.all_reduce(sums)
+        if os.environ.get("PYATM_BENCH_STEP_TIMES"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            step_events.append(ev)
+    hist, sums, tab = reduce_stats(args.warmup, steps_total)
     e1.record()
     barrier()
     launches = nat.launch_count()
+    if step_events and rank == 0:
+        ts = [e0.elapsed_time(ev) for ev in step_events]
+        print("per-step ms:", [round(b - a, 2) for a, b in zip([0.0] + ts[:-1], ts)], file=sys.stderr)
     ms = e0.elapsed_time(e1)
     if world > 1:
         import torch.distributed as td

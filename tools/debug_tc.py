@@ -59,6 +59,10 @@ def run(n, theta_cut, nscreens=1):
     torch.cuda.synchronize()
     print(f"   tc turns-only: {ev0.elapsed_time(ev1) / reps * 1e3 / nscreens:.1f} us per screen (all kernels)")
     e = out[1][0] - out[0][0]
+    k = np.unravel_index(np.argmax(np.abs(e)), e.shape)
+    print('   argmax err at (screen,row,col) =', k, 'row slice around:', np.array2string(e[k[0], k[1], max(0, k[2] - 10):k[2] + 10], precision=2))
+    colmax = np.abs(e).max(axis=(0, 1)); print('   cols with err > 5e-5:', np.nonzero(colmax > 5e-5)[0][:40])
+    rowmax = np.abs(e).max(axis=(0, 2)); print('   rows with err > 5e-5:', np.nonzero(rowmax > 5e-5)[0][:40])
     et = np.abs(np.exp(-2j * np.pi * out[1][1].astype(np.float64)) - np.exp(-2j * np.pi * out[0][1].astype(np.float64)))
     print(f"n={n} theta_cut={theta_cut} m_split={m_split} degree={degree} bound={bound:.2f} nscreens={nscreens}: "
           f"rms(phi_exact)={np.sqrt(np.mean(out[0][0]**2)):.3f} err rms={np.sqrt(np.mean(e**2)):.3e} max={np.abs(e).max():.3e} "

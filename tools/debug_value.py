@@ -59,3 +59,23 @@ print("propagate (numpy coefs)  ms:", timeit(prop))
 rng()
 print("fx stats device:", float(fx.abs().max()), float(fx.std()), "coef absmax", float(cf.abs().max()), "nan?", bool(torch.isnan(cf).any()))
 print("numpy coef absmax", np.abs(hcf).max(), "fx absmax", np.abs(hfx).max())
+
+# ---- how much does NVML polling perturb the GPU? ----
+import threading, pynvml
+pynvml.nvmlInit()
+hd = pynvml.nvmlDeviceGetHandleByIndex(0)
+def poll(kind, period, stop):
+    while not stop[0]:
+        if kind in ("clock", "both"): pynvml.nvmlDeviceGetClockInfo(hd, pynvml.NVML_CLOCK_SM)
+        if kind in ("reasons", "both"): pynvml.nvmlDeviceGetCurrentClocksEventReasons(hd)
+        if kind == "power": pynvml.nvmlDeviceGetPowerUsage(hd)
+        time.sleep(period)
+for kind, period in (("none", 1), ("clock", 0.05), ("reasons", 0.05), ("power", 0.05), ("both", 0.2), ("both", 0.05)):
+    stop = [False]
+    th = threading.Thread(target=poll, args=(kind, period, stop), daemon=True)
+    if kind != "none": th.start()
+    time.sleep(0.3)
+    ms = timeit(full, reps=60)
+    stop[0] = True
+    if kind != "none": th.join()
+    print(f"polling {kind:8s} every {period*1e3:.0f} ms: step {ms:.3f} ms")
