@@ -338,8 +338,15 @@ def run_gpu(args):
         peak, peak_src = measured_peaks()
         alg = 4 * n * n * 8 * B
         name = max(times, key=times.get)
+        traffic = None
+        try:        # dram bytes per launch of the same kernels from the committed ncu capture (scaled to this batch)
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = int(tj[name] * B / tj["batch"])
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": name, "achieved": alg / times[name] / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / times[name] / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                "frac": alg / times[name] / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg,
                 "per_kernel_us": {k: v * 1e6 for k, v in times.items()},
                 "stage_us_per_realization": sum(times.values()) * 1e6 / B,
