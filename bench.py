@@ -119,13 +119,13 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """Samples SM clock and throttle reasons of one GPU during the timed region.  In-process NVML (nvidia_ml_py)
-    every 200 ms (clock + event reasons only).  Polling is deliberately sparse: on these hosts every NVML /
-    nvidia-smi poll stalls the GPU for milliseconds (50 ms polling cost 30 % of the throughput)."""
+    every 20 ms (clock + event reasons).  An external `nvidia-smi -lms` process is avoided: its start-up stalls
+    kernel launches for tens of milliseconds."""
 
     def __init__(self, device):
         self.device, self.rows, self.thread, self.stop_flag = device, [], None, False
         self.err = None
-        self.period = 0.2       # NVML polling itself perturbs the GPU (measured: -30% at 50 ms); keep it sparse
+        self.period = 0.02      # in-process NVML polling does not perturb the kernels (measured, tools/debug_value.py)
 
     def start(self):
         try:
@@ -162,7 +162,7 @@ class ClockSampler:
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: " + str(self.err)]}
         nv = self.nv
-        busy = [r for r in self.rows if t0 is not None and t0 <= r[2] <= t1] or self.rows[-3:]
+        busy = [r for r in self.rows if t0 is not None and t0 <= r[2] <= t1] or self.rows[-3:]      # samples inside the timed region
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake_slowdown": 0x80}
         reasons = sorted(k for k, bit in names.items() if any(r[1] & bit for r in busy))
@@ -243,8 +243,6 @@ def run_gpu(args):
         step_device(i)
     reduce_stats(0, args.warmup)          # also warms up the lazily loaded torch / NCCL kernels of the reduction
     barrier()
-    if rank == 0:
-        sampler.rows.clear()
     nat.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
