@@ -194,6 +194,29 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
     field, table, table2 = buf["field"], buf["table"], buf["table2"]
     desc = path._descriptor((0, 0), through_output=False, from_field=False)
     stream = nat.stream_ptr()
+    stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+    nm = len(nat.MEASURE_NAMES)
+    tab = np.array([[np.float32(r**2), 0, 0] for r in pupils_fixed], dtype=np.float32).reshape(-1, 3)
+    if not pupils_tracked and len(pupils_fixed) <= 4:
+        # statistics only: one C-ABI call per batch; the library reduces inside the final row pass and never
+        # writes the output fields (simulations/simulation.py:89-114 for Beam/PDT records)
+        out_host = np.empty((B, stride), dtype=np.float64)
+        if host is not None:
+            sel = slice(int(mine[0] - first), int(mine[0] - first) + B)
+            hfx = np.ascontiguousarray(host[0][sel].transpose(1, 0, 2))                               # [S][B][M]
+            hfy = np.ascontiguousarray(host[1][sel].transpose(1, 0, 2))
+            hcf = np.ascontiguousarray(host[2][sel].transpose(1, 0, 2)).view(np.float32)
+            nat.check(ctx.lib.pa_simulate_batch(ctx.handle, desc.ref(), B, nat.ptr(hfx), nat.ptr(hfy), nat.ptr(hcf), 0, 0, None, None,
+                                                nat.ptr(tab) if len(tab) else None, len(pupils_fixed), nat.ptr(out_host), stride, stream))
+        else:
+            edges_d, psd_d = ring_tables(ctx, path.phase_screens[0])
+            nat.check(ctx.lib.pa_simulate_batch(ctx.handle, desc.ref(), B, None, None, None, int(gpu.config["seed"]), int(mine[0]),
+                                                nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(tab) if len(tab) else None,
+                                                len(pupils_fixed), nat.ptr(out_host), stride, stream))
+        out = np.empty((B, len(cols)), dtype=np.float64)
+        out[:, :nm] = out_host[:, :nm]
+        out[:, nm:] = out_host[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + len(pupils_fixed)]
+        return out
     if host is not None:
         sel = slice(int(mine[0] - first), int(mine[0] - first) + B)
         fx_d = torch.as_tensor(np.ascontiguousarray(host[0][sel].transpose(1, 0, 2)), device=dev)     # [S][B][M]
@@ -207,13 +230,10 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
         nat.check(ctx.lib.pa_rng_spectrum(ctx.handle, int(gpu.config["seed"]), int(mine[0]), B, 0, S, M, nat.ptr(edges_d),
                                           nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
     nat.check(ctx.lib.pa_propagate(ctx.handle, desc.ref(), nat.ptr(field), B, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
-    stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
-    tab = np.array([[np.float32(r**2), 0, 0] for r in pupils_fixed], dtype=np.float32).reshape(-1, 3)
     tab_d = torch.as_tensor(tab, device=dev) if len(pupils_fixed) else None
     nat.check(ctx.lib.pa_measure(ctx.handle, nat.ptr(field), B, nat.ptr(tab_d), len(pupils_fixed), 0, nat.ptr(table), stride, stream))
     out = np.empty((B, len(cols)), dtype=np.float64)
     t1 = table[:B].cpu().numpy()
-    nm = len(nat.MEASURE_NAMES)
     out[:, :nm] = t1[:, :nm]
     out[:, nm:nm + len(pupils_fixed)] = t1[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + len(pupils_fixed)]
     if pupils_tracked:

@@ -44,6 +44,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+struct SepTable {          // Gaussian source carried through the first leg analytically (separable)
+    double length, wvl, w0, F0;
+    void* dev;             // cplx<T>[n]: p(x) with u1(y,x) = scale * p(y) p(x)
+    double scale_re, scale_im;
+};
+
 struct HTable {
     double length, wvl;
     void* dev;            // cplx<T>[n] permuted transfer-function factor
@@ -64,6 +70,8 @@ struct pa_ctx {
     void* tw = nullptr;                // twiddles
     std::vector<int> perm;             // frequency index held at storage position p
     std::vector<HTable> htabs;
+    std::vector<SepTable> seps;
+    bool sep_first_leg = true;   // complex64 only: start from the analytic first leg (exact identity, float64 1-D transform)
     // workspace (grown on demand, never shrunk)
     void* turns = nullptr; size_t turns_bytes = 0;
     double* P = nullptr; double* Q = nullptr; size_t pq_bytes = 0;
@@ -76,6 +84,7 @@ struct pa_ctx {
     std::vector<TensorMapEntry> tmaps;   // column-pass tensor maps, keyed by (field pointer, batch)
     bool use_tma = true;        // column pass: TMA-fed persistent kernel
     bool rows_tma = false;      // row pass: the direct-access kernel is faster (smem-bound), TMA variant kept for experiments
+    double* rowsums = nullptr; size_t rowsums_bytes = 0;   // per-row sums of the fused final pass
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
     int num_sms = 148;
@@ -225,9 +234,96 @@ static int get_tensor_map(pa_ctx* c, void* field, int batch, const CUtensorMap**
     return PA_OK;
 }
 
+// In-place radix-2 FFT in double precision on the host (tables only; n is a power of two).
+static void host_fft(std::vector<std::complex<double>>& a, bool inverse) {
+    const size_t n = a.size();
+    for (size_t i = 1, j = 0; i < n; ++i) {
+        size_t bit = n >> 1;
+        for (; j & bit; bit >>= 1) j ^= bit;
+        j ^= bit;
+        if (i < j) std::swap(a[i], a[j]);
+    }
+    for (size_t len = 2; len <= n; len <<= 1) {
+        const double ang = 2 * M_PI / (double)len * (inverse ? 1 : -1);
+        for (size_t i = 0; i < n; i += len)
+            for (size_t k = 0; k < len / 2; ++k) {
+                const std::complex<double> w(cos(ang * (double)k), sin(ang * (double)k));
+                const std::complex<double> u = a[i + k], v = a[i + k + len / 2] * w;
+                a[i + k] = u + v;
+                a[i + k + len / 2] = u - v;
+            }
+    }
+    if (inverse)
+        for (auto& z : a) z /= (double)n;
+}
+
+// The Gaussian source is separable, u0(y,x) = amp g(y) g(x) with g(s) = exp(-(1/w0^2 + i k/(2 F0)) s^2), and so is
+// the transfer function, hence the field after the first vacuum leg is  amp e^{ikL} p(y) p(x)  with the 1-D
+// propagation p = IFFT(h * FFT(g)).  p is computed once per (L, source) in float64 on the host; the first row
+// pass then starts from the outer product instead of running a source pass, a column pass and an inverse row
+// transform.  (length <= 0: p = g.)  The only deviation from the reference's arithmetic is that rho^2 is not
+// rounded to float32 (relative 6e-8 in the exponent); complex128 contexts keep the literal path.
+static int get_sep_table(pa_ctx* c, double length, double wvl, double w0, double F0, const SepTable** out) {
+    for (const auto& t : c->seps)
+        if (t.length == length && t.wvl == wvl && t.w0 == w0 && ((t.F0 == F0) || (isinf(t.F0) && isinf(F0)))) {
+            *out = &t;
+            return PA_OK;
+        }
+    const int n = c->n;
+    const double k = 2 * M_PI / wvl;
+    const double aw = 1 / (w0 * w0), ac = isinf(F0) ? 0.0 : 2 * M_PI / wvl / 2 / F0;
+    std::vector<std::complex<double>> g(n);
+    for (int i = 0; i < n; ++i) {
+        const double s2 = (double)c->hx[i] * (double)c->hx[i];
+        g[i] = std::exp(std::complex<double>(-aw * s2, -ac * s2));
+    }
+    SepTable t;
+    t.length = length; t.wvl = wvl; t.w0 = w0; t.F0 = F0; t.dev = nullptr;
+    const double amp = sqrt(2 / M_PI) / w0;
+    t.scale_re = amp;
+    t.scale_im = 0.0;
+    if (length > 0) {
+        host_fft(g, false);
+        const double df = 1 / ((double)n * c->delta);
+        const double coef = (M_PI * length) * (2 * M_PI / k);
+        for (int q = 0; q < n; ++q) {
+            const int qs = q < n / 2 ? q : q - n;
+            const double f = (double)(float)qs * df;
+            const double ph = -(coef * (f * f));
+            g[q] *= std::complex<double>(cos(ph), sin(ph));
+        }
+        host_fft(g, true);
+        const double ang = k * length;
+        t.scale_re = amp * cos(ang);
+        t.scale_im = amp * sin(ang);
+    }
+    PA_CUDA(cudaMalloc(&t.dev, (size_t)n * c->csize()));
+    if (c->prec == 0) {
+        std::vector<float2> h(n);
+        for (int i = 0; i < n; ++i) h[i] = make_float2((float)g[i].real(), (float)g[i].imag());
+        PA_CUDA(cudaMemcpy(t.dev, h.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double2> h(n);
+        for (int i = 0; i < n; ++i) h[i] = make_double2(g[i].real(), g[i].imag());
+        PA_CUDA(cudaMemcpy(t.dev, h.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+    }
+    c->seps.push_back(t);
+    *out = &c->seps.back();
+    return PA_OK;
+}
+
+// request to reduce the output field inside the final row pass (see fft_passes.cuh, MEAS)
+struct FusedMeasure {
+    double* rowsums;
+    const float* pupils_dev;
+    int npupil;
+    int store;       // 0: the field itself is not written back
+    bool done;       // set by the propagator when the final pass did reduce
+};
+
 // ---- pass helpers -----------------------------------------------------------------------------------------
 static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, bool src, const void* turns, double scale,
-                double amp, double aw, double ac, cudaStream_t st) {
+                double amp, double aw, double ac, cudaStream_t st, const SepTable* sep = nullptr, const struct FusedMeasure* fm = nullptr) {
     RowLaunch r;
     r.field = field;
     r.tw = c->tw;
@@ -242,6 +338,13 @@ static int rows(pa_ctx* c, void* field, int batch, bool in_perm, bool out_perm, 
     r.amp = amp;
     r.aw = aw;
     r.ac = ac;
+    r.rowsums = fm ? fm->rowsums : nullptr;
+    r.pupils = fm ? fm->pupils_dev : nullptr;
+    r.npupil = fm ? fm->npupil : 0;
+    r.store = fm ? fm->store : 1;
+    r.sep = sep ? sep->dev : nullptr;
+    r.sep_re = sep ? sep->scale_re : 0.0;
+    r.sep_im = sep ? sep->scale_im : 0.0;
     r.use_tma = c->rows_tma;
     r.num_sms = c->num_sms;
     note(1);
@@ -405,9 +508,11 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
         return PA_ERR_CUDA;
     }
     c->htabs.reserve(256);
+    c->seps.reserve(64);
     c->num_sms = prop.multiProcessorCount;
     c->use_tma = !(getenv("PYATM_FFT_DIRECT") && atoi(getenv("PYATM_FFT_DIRECT")) != 0);
     c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") && atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0;
+    c->sep_first_leg = !(getenv("PYATM_NO_ANALYTIC_LEG") && atoi(getenv("PYATM_NO_ANALYTIC_LEG")) != 0);
     *out = c;
     return PA_OK;
 }
@@ -415,11 +520,13 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
 int pa_ctx_destroy(pa_ctx* c) {
     if (!c) return PA_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err};
+    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& h : c->htabs)
         if (h.dev) cudaFree(h.dev);
+    for (auto& t : c->seps)
+        if (t.dev) cudaFree(t.dev);
     delete c;
     return PA_OK;
 }
@@ -439,6 +546,9 @@ int pa_ctx_set_axes(pa_ctx* c, const float* x_host, const float* y_host, double 
             if (h.dev) cudaFree(h.dev);
         c->htabs.clear();
     }
+    for (auto& t : c->seps)
+        if (t.dev) cudaFree(t.dev);
+    c->seps.clear();
     c->delta = delta;
     c->axes_set = true;
     return PA_OK;
@@ -577,8 +687,8 @@ int pa_fft_pass(pa_ctx* c, void* field, int batch, int kind, const void* turns, 
 
 // Token stream of one realization: SRC, then for every screen [leg] screen, then [closing leg].  A leg is
 // FFT_x | columns | IFFT_x; all row-level tokens between two column passes are fused into one k_rows launch.
-int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const float* fx, const float* fy, const float* coef,
-                 void* stream) {
+static int propagate_impl(pa_ctx* c, const pa_path* p, void* field, int batch, const float* fx, const float* fy, const float* coef,
+                          void* stream, FusedMeasure* fm) {
     PA_REQUIRE(c && p && field && batch > 0, "bad arguments to pa_propagate");
     PA_REQUIRE(p->n_screens >= 0 && p->leg_lengths_host, "bad path description");
     PA_REQUIRE(p->n_screens == 0 || (fx && fy && coef && p->screen_scale_host), "screen coefficients missing");
@@ -599,9 +709,13 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
     bool have_field = p->from_field != 0;   // false: the source has not been materialised yet
     bool perm = false;         // true: field is in row-spectrum form awaiting IFFT_x
     // one fused row launch: [SRC | IFFT_x]? [screen]? [FFT_x]?
-    auto row_launch = [&](bool want_perm_out, const void* turns, double scale) -> int {
+    const SepTable* start_sep = nullptr;   // set when the source is carried analytically through the first leg
+    const bool can_fuse = fm != nullptr && (c->n / c->e) >= 32;
+    auto row_launch = [&](bool want_perm_out, const void* turns, double scale, bool final_pass = false) -> int {
         const bool src = !have_field;
-        int r = rows(c, field, batch, perm, want_perm_out, src, turns, scale, amp, aw, ac, st);
+        const bool fuse = final_pass && can_fuse && perm && !want_perm_out && !src;
+        int r = rows(c, field, batch, perm, want_perm_out, src, turns, scale, amp, aw, ac, st, src ? start_sep : nullptr, fuse ? fm : nullptr);
+        if (fuse) fm->done = true;
         have_field = true;
         perm = want_perm_out;
         return r;
@@ -612,9 +726,14 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
                        nullptr, 0, p->screen_method, p->coef_bound, st);
     };
 
+    const bool analytic_first_leg = !have_field && S > 0 && c->prec == PA_C64 && c->sep_first_leg;
+    if (analytic_first_leg) {
+        rc = get_sep_table(c, p->leg_lengths_host[0], p->wvl, p->w0, p->F0, &start_sep);
+        if (rc) return rc;
+    }
     for (int i = 0; i < S; ++i) {
         const double L = p->leg_lengths_host[i];
-        if (L > 0) {
+        if (L > 0 && !(i == 0 && analytic_first_leg)) {
             if (!perm) {                       // leading FFT_x of this leg was not fused into a previous launch
                 rc = row_launch(true, nullptr, 1.0);
                 if (rc) return rc;
@@ -628,7 +747,7 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
         double scale = p->screen_scale_host[i];
         const bool fuse_next = Lnext > 0;
         if (i == S - 1 && !fuse_next) scale *= p->final_scale;
-        rc = row_launch(fuse_next, c->turns, scale);
+        rc = row_launch(fuse_next, c->turns, scale, i == S - 1 && !fuse_next);
         if (rc) return rc;
     }
     const double Llast = p->leg_lengths_host[S];
@@ -639,13 +758,18 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
         }
         rc = cols(c, field, batch, Llast, p->wvl, st);
         if (rc) return rc;
-        rc = row_launch(false, nullptr, p->final_scale);
+        rc = row_launch(false, nullptr, p->final_scale, true);
         if (rc) return rc;
     } else if (S == 0) {
         rc = row_launch(false, nullptr, p->final_scale);
         if (rc) return rc;
     }
     return PA_OK;
+}
+
+int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const float* fx, const float* fy, const float* coef,
+                 void* stream) {
+    return propagate_impl(c, p, field, batch, fx, fy, coef, stream, nullptr);
 }
 
 static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host,
@@ -671,8 +795,23 @@ static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* 
             if (rc) return rc;
         }
     }
-    rc = pa_propagate(c, p, c->field, batch, fx, fy, coef, st);
+    // statistics only: reduce inside the final row pass and do not write the output field at all
+    FusedMeasure fm{nullptr, pupils_dev, npupil, 0, false};
+    FusedMeasure* fmp = nullptr;
+    if (npupil <= kFusedPupils && !(getenv("PYATM_NO_FUSED_MEASURE") && atoi(getenv("PYATM_NO_FUSED_MEASURE")) != 0)) {
+        rc = grow((void**)&c->rowsums, &c->rowsums_bytes, (size_t)batch * n * kRowSums * sizeof(double));
+        if (rc) return rc;
+        fm.rowsums = c->rowsums;
+        fmp = &fm;
+    }
+    rc = propagate_impl(c, p, c->field, batch, fx, fy, coef, st, fmp);
     if (rc) return rc;
+    if (fm.done) {
+        PA_REQUIRE(out_stride >= kMeasureHead + npupil, "out_stride too small");
+        note(1);
+        return check_launch(launch_measure_rows(c->rowsums, c->y, n, batch, c->delta * c->delta, npupil, table_dev, out_stride, st),
+                            "measure (fused)");
+    }
     return pa_measure(c, c->field, batch, pupils_dev, npupil, 0, table_dev, out_stride, st);
 }
 

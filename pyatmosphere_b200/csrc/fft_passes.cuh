@@ -12,6 +12,7 @@
 // read+write sweeps of the field.
 #pragma once
 #include "fft_core.cuh"
+#include "internal_measure.h"
 
 namespace pa {
 
@@ -61,10 +62,21 @@ template <typename T> struct RowArgs {
     const float* x;
     const float* y;
     double amp, aw, ac;
+    // separable start (SRC = true and sep != nullptr): the field is  sep_scale * sep[row] * sep[column]; used for
+    // the Gaussian source carried analytically through the first vacuum leg (see api.cu: first_leg_table)
+    const cplx<T>* sep;
+    T sep_re, sep_im;
+    // fused reductions (MEAS = true, natural-order output): per-row sums {I, I x, I x^2, I [inside aperture p]} are
+    // written to rowsums[row][kRowSums]; k_measure_finish_rows folds them with the y weights.  store = 0 skips
+    // writing the field itself (Monte-Carlo runs that only need the statistics).
+    double* rowsums;
+    const float* pupils;   // [npupil][3] {r^2, sx, sy} float32, npupil <= kFusedPupils
+    int npupil;
+    int store;
 };
 
 // One CTA = FPB rows, N/E threads per row.
-template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC>
+template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC, bool MEAS = false>
 __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
     using C = cplx<T>;
     constexpr int TPF = N / E;
@@ -78,6 +90,11 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
     C v[E];
 
     if constexpr (SRC) {
+      if (a.sep != nullptr) {
+        const C sy = cmul(ldg_c<T>(a.sep + row % N), mkc<T>(a.sep_re, a.sep_im));
+#pragma unroll
+        for (int i = 0; i < E; ++i) v[i] = cmul(ldg_c<T>(a.sep + reg_pos<N, E, 0>(t, i)), sy);
+      } else {
         const float yv = a.y[row % N];
         const float y2 = __fmul_rn(yv, yv);
 #pragma unroll
@@ -94,6 +111,7 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
                 v[i] = mkc<T>((T)mag, (T)0);
             }
         }
+      }
     } else if constexpr (IN_PERM) {
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = ptr[io_pos<N, E>(t, i)];      // spectrum in storage order
@@ -126,8 +144,61 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
 #pragma unroll
         for (int i = 0; i < E; ++i) ptr[io_pos<N, E>(t, i)] = v[i];
     } else {
+        if (!MEAS || a.store) {
 #pragma unroll
-        for (int i = 0; i < E; ++i) ptr[reg_pos<N, E, 0>(t, i)] = v[i];
+            for (int i = 0; i < E; ++i) ptr[reg_pos<N, E, 0>(t, i)] = v[i];
+        }
+        if constexpr (MEAS) {
+            // same arithmetic as k_measure_partial (measure.cu): intensity and x-weights in the field's precision,
+            // aperture predicate in float32 without FMA contraction (pupils.py:10)
+            const float yv = a.y[row % N];
+            float pr2[kFusedPupils], psx[kFusedPupils], dy2[kFusedPupils];
+            T acc[kRowSums];
+#pragma unroll
+            for (int q = 0; q < kRowSums; ++q) acc[q] = 0;
+#pragma unroll
+            for (int p = 0; p < kFusedPupils; ++p) {
+                const bool on = p < a.npupil;
+                pr2[p] = on ? a.pupils[3 * p] : -1.0f;
+                psx[p] = on ? a.pupils[3 * p + 1] : 0.0f;
+                const float dy = __fadd_rn(yv, on ? a.pupils[3 * p + 2] : 0.0f);
+                dy2[p] = __fmul_rn(dy, dy);
+            }
+#pragma unroll
+            for (int i = 0; i < E; ++i) {
+                const float xv = a.x[reg_pos<N, E, 0>(t, i)];
+                const T in = v[i].x * v[i].x + v[i].y * v[i].y;
+                acc[0] += in;
+                acc[1] += in * (T)xv;
+                acc[2] += in * ((T)xv * (T)xv);
+#pragma unroll
+                for (int p = 0; p < kFusedPupils; ++p) {
+                    const float dx = __fsub_rn(xv, psx[p]);
+                    acc[3 + p] += (__fadd_rn(__fmul_rn(dx, dx), dy2[p]) <= pr2[p]) ? in : (T)0;
+                }
+            }
+            // reduce over the N/E threads of the row: shuffles, then one slot per warp in shared memory
+            double red[kRowSums];
+#pragma unroll
+            for (int q = 0; q < kRowSums; ++q) {
+                double r = (double)acc[q];
+                for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+                red[q] = r;
+            }
+            constexpr int WPR = TPF / 32 > 0 ? TPF / 32 : 1;      // warps per row (TPF >= 32 in the fused configuration)
+            __syncthreads();                                       // exchanges are over: reuse the row's smem
+            double* sred = reinterpret_cast<double*>(smem_raw) + (size_t)f * (N * sizeof(C) / sizeof(double));
+            if ((t & 31) == 0) {
+#pragma unroll
+                for (int q = 0; q < kRowSums; ++q) sred[(t >> 5) * kRowSums + q] = red[q];
+            }
+            __syncthreads();
+            if (t < kRowSums) {
+                double r = 0.0;
+                for (int w = 0; w < WPR; ++w) r += sred[w * kRowSums + t];
+                a.rowsums[(size_t)row * kRowSums + t] = r;
+            }
+        }
     }
 }
 

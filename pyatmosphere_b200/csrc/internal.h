@@ -23,6 +23,12 @@ struct RowLaunch {
     const float* x;
     const float* y;
     double amp, aw, ac;
+    const void* sep;      // separable start table (cplx<T>[n]) or null
+    double* rowsums;      // fused reductions (in_perm && !out_perm only): per-row sums, or null
+    const float* pupils;
+    int npupil;
+    int store;
+    double sep_re, sep_im;
     bool use_tma;         // persistent TMA-fed variant (ignored where it does not exist)
     int num_sms;
 };

@@ -112,6 +112,58 @@ int launch_measure(int prec, const MeasureLaunch& a, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
+// out[b] from the per-row sums of the fused final row pass: rowsums[b*n + i] = {S0, S1, S2, P0..P3}(row i)
+__global__ void __launch_bounds__(256) k_measure_finish_rows(const double* rowsums, const float* y, int n, double delta2, int npupil,
+                                                             double* out, int out_stride) {
+    const int b = blockIdx.x;
+    double acc[kRawMoments + kFusedPupils];
+#pragma unroll
+    for (int q = 0; q < kRawMoments + kFusedPupils; ++q) acc[q] = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double* r = rowsums + ((size_t)b * n + i) * kRowSums;
+        const double yv = (double)y[i];
+        acc[0] += r[0];
+        acc[1] += r[1];
+        acc[2] += yv * r[0];
+        acc[3] += r[2];
+        acc[4] += yv * r[1];
+        acc[5] += yv * yv * r[0];
+#pragma unroll
+        for (int p = 0; p < kFusedPupils; ++p) acc[kRawMoments + p] += r[3 + p];
+    }
+    __shared__ double red[8][kRawMoments + kFusedPupils];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < kRawMoments + kFusedPupils; ++q) {
+        double v = acc[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[warp][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot[kRawMoments + kFusedPupils];
+        for (int q = 0; q < kRawMoments + kFusedPupils; ++q) {
+            double v = 0.0;
+            for (int w = 0; w < 8; ++w) v += red[w][q];
+            tot[q] = v * delta2;
+        }
+        double* o = out + (size_t)b * out_stride;
+        const double eta = tot[0], mx = tot[1], my = -tot[2], mx2 = tot[3], mxy = -tot[4], my2 = tot[5];
+        o[0] = eta; o[1] = mx; o[2] = my; o[3] = mx2; o[4] = mxy; o[5] = my2;
+        const double r0 = sqrt(mx * mx + my * my);
+        const double c = mx / r0, s = my / r0;
+        o[6] = c * c * mx2 + 2.0 * c * s * mxy + s * s * my2;
+        o[7] = 0.0;
+        for (int p = 0; p < npupil; ++p) o[kMeasureHead + p] = tot[kRawMoments + p];
+    }
+}
+
+int launch_measure_rows(const double* rowsums, const float* y, int n, int batch, double delta2, int npupil, double* out, int out_stride,
+                        cudaStream_t st) {
+    k_measure_finish_rows<<<batch, 256, 0, st>>>(rowsums, y, n, delta2, npupil, out, out_stride);
+    return (int)cudaGetLastError();
+}
+
 // ---- element-wise helpers ----------------------------------------------------------------------------------
 template <typename T> __global__ void k_intensity(const cplx<T>* u, T* out, size_t count) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {

@@ -387,3 +387,26 @@ def test_full_size_turbulent_energy_and_determinism():
             np.random.seed(1)
             assert np.array_equal(ch.run(pupil=False).get(), fields[dtype])
     assert rel_l2(fields["complex64"], fields["complex128"]) < 1e-5
+
+
+def test_fused_statistics_route_equals_literal_route(monkeypatch):
+    """The Monte-Carlo route (analytic first leg, reductions fused into the final row pass, no field written) gives
+    the same records as the literal route (source pass, six full legs, separate measure sweep)."""
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    g = load_golden("quick256")
+    p = dict(g["params"], n=512, delta=2e-3)       # 512: smallest size with the fused final pass
+    tables = {}
+    for tag, env in (("fused", {}), ("literal", {"PYATM_NO_FUSED_MEASURE": "1", "PYATM_NO_ANALYTIC_LEG": "1"})):
+        for k in ("PYATM_NO_FUSED_MEASURE", "PYATM_NO_ANALYTIC_LEG"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        nat.clear_contexts()
+        pa = _pa("complex64", rng="philox", seed=7, batch=4)
+        ch = build_channel(pa, p)
+        cols = eng.table_columns([p["pupil"], 0.05], [])
+        tables[tag] = eng.simulate_realizations(ch, 0, 4, np.arange(4), [p["pupil"], 0.05], [])
+        assert tables[tag].shape == (4, len(cols))
+    nat.clear_contexts()
+    assert np.allclose(tables["fused"], tables["literal"], rtol=2e-5, atol=1e-8)
+    assert np.all(tables["fused"][:, 0] == pytest.approx(1.0, abs=1e-4))
