@@ -11,24 +11,32 @@ from . import _native as nat
 from . import gpu
 
 SCREEN_METHODS = {"exact": nat.PA_SCREEN_EXACT, "tc": nat.PA_SCREEN_TC}
+MAX_DEGREE = 63
+
+
+TC_MIN_GRID = 1024          # 'auto' uses the tensor-core screens from this grid size on
+TC_NODE_SPACING = 16        # columns between exact polynomial evaluations in the tensor-core epilogue (screen_tc.cu)
 
 
 def screen_method(n: int) -> int:
     """Resolve gpu.config['screen_method'] for a grid of size n."""
     name = gpu.config["screen_method"]
     if name == "auto":
-        name = "tc" if (gpu.precision() == 0 and n % 256 == 0) else "exact"
+        name = "tc" if (gpu.precision() == 0 and n % 256 == 0 and n >= TC_MIN_GRID) else "exact"
     if name == "tc" and (gpu.precision() != 0 or n % 256 != 0):
         raise ValueError("screen_method 'tc' needs dtype complex64 and a grid size that is a multiple of 256")
     return SCREEN_METHODS[name]
 
 
 def theta_cut(n: int) -> float:
+    """Largest phase argument (rad, over the whole grid) of the rings that are summed as a polynomial.
+    The tensor-core epilogue interpolates that polynomial between nodes TC_NODE_SPACING columns apart, which needs
+    the phase of its fastest harmonic to advance by <= 0.16 rad per node: theta_cut <= 0.16 * n / (2 * spacing)."""
     tc = gpu.config["theta_cut"]
-    if tc is None:
-        return 10.0 if screen_method(n) == nat.PA_SCREEN_TC else 2.0
-    return float(tc)
-MAX_DEGREE = 63
+    if screen_method(n) == nat.PA_SCREEN_TC:
+        limit = 0.16 * n / (2 * TC_NODE_SPACING)
+        return min(10.0 if tc is None else float(tc), limit)
+    return 2.0 if tc is None else float(tc)
 
 
 def channel_context(channel) -> nat.Context:

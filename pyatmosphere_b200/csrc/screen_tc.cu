@@ -34,8 +34,7 @@ constexpr int STAGE_BYTES = P_STAGE + Q_STAGE;
 constexpr int STAGES = 3;
 constexpr int EPI_WARPS = 8;                  // two per TMEM lane quarter, each takes half of the 256 columns
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
-constexpr int XPAD = 8;                       // column coordinates staged for [-8, TN + 24) around the tile
-constexpr int SX_LEN = TN + 32;
+constexpr int NODE_SP = 16;                   // exact polynomial evaluation every 16th column
 constexpr float Q_SCALE = 16.0f;     // P is scaled by a.p_scale (power of two chosen on the host from the coefficient bound)
 constexpr uint32_t SPIN_LIMIT = 1u << 28;
 
@@ -97,6 +96,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// 32 consecutive accumulator columns of this thread's TMEM lane; asynchronous: pair with tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // instruction descriptor: fp32 accumulate, fp16 A and B, both K-major, M = 128, N = 256
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -182,6 +196,25 @@ __global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U) {
     U[((size_t)s * (D + 1) + p) * a.n + i] = fma(u1, yh, u0);
 }
 
+// 6-point Lagrange weights for nodes -2..3 at s = r/16 (sum to one; applied to differences from node 0)
+__device__ constexpr float kLag[16][6] = {
+    {0.0000000000e+00f, 0.0000000000e+00f, 1.0000000000e+00f, 0.0000000000e+00f, 0.0000000000e+00f, 0.0000000000e+00f},
+    {2.9526948929e-03f, -2.8658509254e-02f, 9.7438931465e-01f, 6.4959287643e-02f, -1.5715956688e-02f, 2.0731687546e-03f},
+    {5.5274963379e-03f, -5.2204132080e-02f, 9.3967437744e-01f, 1.3423919678e-01f, -3.1322479248e-02f, 4.0855407715e-03f},
+    {7.6850652695e-03f, -7.0783495903e-02f, 8.9659094810e-01f, 2.0690560341e-01f, -4.6375393867e-02f, 5.9772729874e-03f},
+    {9.3994140625e-03f, -8.4594726562e-02f, 8.4594726562e-01f, 2.8198242188e-01f, -6.0424804688e-02f, 7.6904296875e-03f},
+    {1.0656952858e-02f, -9.3882679939e-02f, 7.8861451149e-01f, 3.5846114159e-01f, -7.3019862175e-02f, 9.1699361801e-03f},
+    {1.1455535889e-02f, -9.8934173584e-02f, 7.2551727295e-01f, 4.3531036377e-01f, -8.3713531494e-02f, 1.0364532471e-02f},
+    {1.1803507805e-02f, -1.0007321835e-01f, 6.5762400627e-01f, 5.1148533821e-01f, -9.2067360878e-02f, 1.1227726936e-02f},
+    {1.1718750000e-02f, -9.7656250000e-02f, 5.8593750000e-01f, 5.8593750000e-01f, -9.7656250000e-02f, 1.1718750000e-02f},
+    {1.1227726936e-02f, -9.2067360878e-02f, 5.1148533821e-01f, 6.5762400627e-01f, -1.0007321835e-01f, 1.1803507805e-02f},
+    {1.0364532471e-02f, -8.3713531494e-02f, 4.3531036377e-01f, 7.2551727295e-01f, -9.8934173584e-02f, 1.1455535889e-02f},
+    {9.1699361801e-03f, -7.3019862175e-02f, 3.5846114159e-01f, 7.8861451149e-01f, -9.3882679939e-02f, 1.0656952858e-02f},
+    {7.6904296875e-03f, -6.0424804688e-02f, 2.8198242188e-01f, 8.4594726562e-01f, -8.4594726562e-02f, 9.3994140625e-03f},
+    {5.9772729874e-03f, -4.6375393867e-02f, 2.0690560341e-01f, 8.9659094810e-01f, -7.0783495903e-02f, 7.6850652695e-03f},
+    {4.0855407715e-03f, -3.1322479248e-02f, 1.3423919678e-01f, 9.3967437744e-01f, -5.2204132080e-02f, 5.5274963379e-03f},
+    {2.0731687546e-03f, -1.5715956688e-02f, 6.4959287643e-02f, 9.7438931465e-01f, -2.8658509254e-02f, 2.9526948929e-03f}};
+
 // ---- contraction + epilogue ---------------------------------------------------------------------------------
 struct TcArgs {
     ScreenLaunch a;
@@ -200,10 +233,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     const ScreenLaunch& a = g.a;
     unsigned char* stage_base = smem;                                        // STAGES * STAGE_BYTES
     double* sU = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);     // [(D+1)][128] row coefficients of this tile
-    double* sX = sU + (size_t)SU_ROWS * TM;                                   // [256] normalised column coordinates
+    float* sX = reinterpret_cast<float*>(sU + (size_t)SU_ROWS * TM);          // [256] float32 jitter of the column axis (normalised)
     const int D = a.degree;
     const double out_scale = 1.0 / (a.p_scale * (double)Q_SCALE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + ((size_t)SU_ROWS * TM + SX_LEN) * sizeof(double));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + ((size_t)SU_ROWS * TM + TN / 2) * sizeof(double));
     // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -299,16 +332,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM lane = output row; float64 polynomial + reduction to turns =====
-        // The low-ring polynomial is smooth on the scale of a few pixels (its highest harmonic has a wavelength of
-        // ~1000 pixels), so it is evaluated exactly (Horner, degree D) only at every 4th column and filled in
-        // between with 6-point Lagrange interpolation (weights are exact binary fractions; the interpolation
-        // error ~ (2 pi f 4 delta)^6 is far below 1e-9 rad).  This cuts the float64 work -- the bound of this
-        // epilogue: B200 issues 32 DFMA/clk/SM -- by 2.2x.
+        // ===== epilogue: TMEM lane = output row; polynomial of the low rings + reduction to turns =====
+        // B200 issues only 32 DFMA/clk/SM, so float64 work bounds this epilogue.  The low-ring polynomial is smooth
+        // on the scale of tens of pixels (its highest harmonic has a wavelength of ~1000 pixels), so it is evaluated
+        // exactly (float64 Horner, degree D) only at every 16th column; in between, the DIFFERENCE from the nearest
+        // node (a few radians at most) is interpolated in float32 with 6-point Lagrange weights, and the node value
+        // itself is reduced mod 2 pi in float64.  Measured against the float64 path: < 2e-7 rad.
         const int ew = warp & 3;                       // TMEM lane quarter this warp may read
         const int ch = (warp - 4) >> 2;                // which half of the 256 columns
         const int et = threadIdx.x - 128;              // index among the epilogue threads
         const int row_in_tile = ew * 32 + lane;
+        const float out_scale_f = (float)out_scale;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
@@ -318,16 +352,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");     // previous tile's readers are done
             for (int p = ch; p <= D; p += 2) sU[p * TM + row_in_tile] = __ldg(U + (size_t)p * n);
             // Column coordinates.  The reference's axis is float32 (x_j = fl32(j * delta) + shift), i.e. a uniform
-            // axis plus a rounding jitter of ~1e-7 m.  The polynomial is evaluated exactly at nodes of the UNIFORM
-            // axis xu_j = x_0 + j * (x_{n-1} - x_0)/(n-1) + shift, interpolated there, and the jitter of every pixel
-            // is put back to first order: phi(x_j) = phi(xu_j) + (x_j - xu_j) * dphi/dx  (second order ~1e-14).
+            // axis plus a rounding jitter of ~1e-7 m.  Nodes sit on the UNIFORM axis xu_j = x_0 + j (x_{n-1}-x_0)/(n-1)
+            // + shift, and the jitter of every pixel is put back to first order:
+            // phi(x_j) = phi(xu_j) + (x_j - xu_j) dphi/dx   (second order ~1e-14).
             const double x_first = (double)__ldg(a.x) + (double)a.shift_x;
             const double dxu = ((double)__ldg(a.x + n - 1) - (double)__ldg(a.x)) / (double)(n - 1);
-            for (int e = et; e < SX_LEN; e += 32 * EPI_WARPS) {      // sX = actual minus uniform coordinate (normalised)
-                const int jj = cb * TN - XPAD + e;
-                double dev = 0.0;
-                if (jj >= 0 && jj < n) dev = (double)__fadd_rn(__ldg(a.x + jj), a.shift_x) - (x_first + dxu * (double)jj);
-                sX[e] = dev * a.inv_x0;
+            if (et < TN) {
+                const int jj = cb * TN + et;
+                sX[et] = (float)(((double)__fadd_rn(__ldg(a.x + jj), a.shift_x) - (x_first + dxu * (double)jj)) * a.inv_x0);
             }
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
             const double* su = sU + row_in_tile;
@@ -338,78 +370,76 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             for (int half = 0; half < 2; ++half) {
                 if (g.swap_lbo_sbo & 8) break;
                 const int cbase = ch * (TN / 2) + half * 64;            // first of the 64 columns of this round
-                // exact values at the 21 nodes cbase + 4k, k = -2..18  (node k is e[k + 2])
-                double e[21];
-                if (D >= 0) {
+                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + cbase);
+                uint32_t acc0[32], acc1[32];
+                tmem_ld32_async(t_row, acc0);                            // in flight during the Horner evaluations below
+                // exact values at the 9 nodes cbase + 16 (kk - 2), kk = 0..8
+                double e[9];
+                {
+                    double xn[9];
 #pragma unroll
-                    for (int b7 = 0; b7 < 3; ++b7) {
-                        double xn[7], acc7[7];
-#pragma unroll
-                        for (int t = 0; t < 7; ++t) {
-                            xn[t] = (x_first + dxu * (double)(cb * TN + cbase + 4 * (7 * b7 + t - 2))) * a.inv_x0;
-                            acc7[t] = 0.0;
-                        }
+                    for (int t = 0; t < 9; ++t) {
+                        xn[t] = (x_first + dxu * (double)(cb * TN + cbase + NODE_SP * (t - 2))) * a.inv_x0;
+                        e[t] = 0.0;
+                    }
+                    if (!(g.swap_lbo_sbo & 32)) {
                         int p = D;
                         for (; p >= 1; p -= 2) {
                             const double u0 = su[p * TM], u1 = su[(p - 1) * TM];
 #pragma unroll
-                            for (int t = 0; t < 7; ++t) acc7[t] = fma(acc7[t], xn[t], u0);
+                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u0);
 #pragma unroll
-                            for (int t = 0; t < 7; ++t) acc7[t] = fma(acc7[t], xn[t], u1);
+                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u1);
                         }
                         if (p == 0) {
                             const double u0 = su[0];
 #pragma unroll
-                            for (int t = 0; t < 7; ++t) acc7[t] = fma(acc7[t], xn[t], u0);
+                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u0);
                         }
-#pragma unroll
-                        for (int t = 0; t < 7; ++t) e[7 * b7 + t] = acc7[t];
                     }
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 21; ++t) e[t] = 0.0;
                 }
-                const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + cbase);
                 const int j0 = cb * TN + cbase;
                 float* turns = a.turns ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
+                const double inv_h = 1.0 / ((double)NODE_SP * dxu * a.inv_x0);   // 1 / node spacing in normalised units
+                tmem_wait_ld();                                          // first 32 accumulator columns have arrived
+                tmem_ld32_async(t_row + 32u, acc1);                      // next 32 travel while these are finished
 #pragma unroll
-                for (int gq = 0; gq < 8; ++gq) {                         // 8 columns = 2 intervals per TMEM load
-                    float acc[8];
-                    tmem_ld8(t_row + (uint32_t)(8 * gq), acc);
-                    double pl[8];
-                    const double inv_h = 1.0 / (4.0 * dxu * a.inv_x0);   // 1 / node spacing in normalised units
+                for (int k = 0; k < 4; ++k) {                            // interval between nodes k and k+1: 16 columns
+                    if (k == 2) tmem_wait_ld();
+                    const double z0 = e[k + 2];
+                    double tz = z0 * 0.15915494309189533576888376;
+                    tz -= rint(tz);
+                    const float t1f = (float)tz;                         // node value in turns, reduced in float64
+                    const float d0 = (float)(e[k] - z0), d1 = (float)(e[k + 1] - z0), d3 = (float)(e[k + 3] - z0);
+                    const float d4 = (float)(e[k + 4] - z0), d5 = (float)(e[k + 5] - z0);
+                    const float slope = (float)((e[k + 3] - z0) * inv_h);
+                    float tv[16], dv[16];
 #pragma unroll
-                    for (int iv = 0; iv < 2; ++iv) {
-                        const int k = 2 * gq + iv;                       // interval between nodes k and k+1
-                        const double m2 = e[k], m1 = e[k + 1], z0 = e[k + 2], p1 = e[k + 3], p2 = e[k + 4], p3 = e[k + 5];
-                        const double slope = (p1 - z0) * inv_h;
-                        pl[4 * iv] = z0;
-                        pl[4 * iv + 1] = 0.0093994140625 * m2 - 0.0845947265625 * m1 + 0.845947265625 * z0 + 0.281982421875 * p1 -
-                                         0.0604248046875 * p2 + 0.0076904296875 * p3;
-                        pl[4 * iv + 2] = 0.01171875 * (m2 + p3) - 0.09765625 * (m1 + p2) + 0.5859375 * (z0 + p1);
-                        pl[4 * iv + 3] = 0.0076904296875 * m2 - 0.0604248046875 * m1 + 0.281982421875 * z0 + 0.845947265625 * p1 -
-                                         0.0845947265625 * p2 + 0.0093994140625 * p3;
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) pl[4 * iv + r] = fma(sX[cbase + 4 * k + r + XPAD], slope, pl[4 * iv + r]);
-                    }
-                    float tv[8];
-                    double ph[8];
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        ph[c] = fma((double)acc[c], out_scale, pl[c]);
-                        const double tt = ph[c] * 0.15915494309189533576888376;
-                        tv[c] = (float)(tt - rint(tt));
+                    for (int r = 0; r < 16; ++r) {
+                        const int c = 16 * k + r;
+                        const float accv = __uint_as_float(c < 32 ? acc0[c & 31] : acc1[c & 31]);
+                        float delta = kLag[r][0] * d0;
+                        delta = fmaf(kLag[r][1], d1, delta);
+                        delta = fmaf(kLag[r][3], d3, delta);
+                        delta = fmaf(kLag[r][4], d4, delta);
+                        delta = fmaf(kLag[r][5], d5, delta);
+                        delta = fmaf(sX[cbase + c], slope, delta);
+                        dv[r] = fmaf(accv, out_scale_f, delta);          // phase minus the node value (a few radians)
+                        float tt = fmaf(dv[r], 0.15915494309189533577f, t1f);
+                        tv[r] = tt - rintf(tt);
                     }
                     if (turns) {
-                        *reinterpret_cast<float4*>(turns + 8 * gq) = make_float4(tv[0], tv[1], tv[2], tv[3]);
-                        *reinterpret_cast<float4*>(turns + 8 * gq + 4) = make_float4(tv[4], tv[5], tv[6], tv[7]);
-                    }
-                    if (a.phi) {
-                        const size_t o = ((size_t)s * n + i) * n + j0 + 8 * gq;
 #pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            if (a.phi_f64) ((double*)a.phi)[o + c] = ph[c];
-                            else ((float*)a.phi)[o + c] = (float)ph[c];
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(turns + 16 * k + 4 * q) = make_float4(tv[4 * q], tv[4 * q + 1], tv[4 * q + 2], tv[4 * q + 3]);
+                    }
+                    if (a.phi) {                                         // full phase requested (generator / inspection path)
+                        const size_t o = ((size_t)s * n + i) * n + j0 + 16 * k;
+#pragma unroll
+                        for (int r = 0; r < 16; ++r) {
+                            const double ph = z0 + (double)dv[r];
+                            if (a.phi_f64) ((double*)a.phi)[o + r] = ph;
+                            else ((float*)a.phi)[o + r] = (float)ph;
                         }
                     }
                 }
@@ -426,7 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     }
 }
 
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ((kMaxPolyDegree + 1) * TM + SX_LEN) * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ((kMaxPolyDegree + 1) * TM + TN / 2) * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
 
 }  // namespace tc
 

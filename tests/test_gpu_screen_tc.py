@@ -29,7 +29,8 @@ def test_auto_method_selection():
     from pyatmosphere_b200 import _engine as eng, _native as nat
     pa.gpu.config.update(dtype="complex64", screen_method="auto", theta_cut=None)
     assert eng.screen_method(2048) == nat.PA_SCREEN_TC and eng.screen_method(128) == nat.PA_SCREEN_EXACT
-    assert eng.theta_cut(2048) == 10.0 and eng.theta_cut(128) == 2.0
+    assert eng.screen_method(1024) == nat.PA_SCREEN_TC and eng.screen_method(512) == nat.PA_SCREEN_EXACT
+    assert eng.theta_cut(2048) == 10.0 and eng.theta_cut(128) == 2.0 and eng.theta_cut(1024) == pytest.approx(5.12)
     pa.gpu.config.update(dtype="complex128")
     assert eng.screen_method(2048) == nat.PA_SCREEN_EXACT
     pa.gpu.config.update(screen_method="tc")
@@ -37,9 +38,10 @@ def test_auto_method_selection():
         eng.screen_method(2048)
 
 
-@pytest.mark.parametrize("theta_cut", [0.0, 2.0, 10.0])
+@pytest.mark.parametrize("theta_cut", [0.5, 1.0, 10.0])
 def test_tc_screen_vs_oracle_256(theta_cut):
-    """quick256 fixture (M = 1024 rings, QuickChannel spectrum): tensor-core phase vs float64 evaluation."""
+    """quick256 fixture (M = 1024 rings, QuickChannel spectrum), tensor-core method forced on a 256^2 grid (the host
+    clamps theta_cut to 1.28 there): phase vs float64 evaluation, tolerance relative to what goes through fp32."""
     import pyatmosphere_b200 as pa
     from pyatmosphere_b200.utils import PolarDiscreteFunction
     pa.gpu.config.update(dtype="complex64", screen_method="tc", theta_cut=theta_cut)
@@ -94,15 +96,17 @@ def test_tc_matches_exact_path_full_size():
 
 @pytest.mark.parametrize("name", ["quick256"])
 def test_channel_run_with_tc_screens(name):
+    """The fixture's physical channel on a 1024^2 grid of the same extent (the tensor-core path starts at 1024):
+    same seed -> same coefficients; checked against the float64 oracle evaluated on that grid."""
     import pyatmosphere_b200 as pa
     pa.gpu.config.update(dtype="complex64", screen_method="auto", theta_cut=None)
     g = load_golden(name)
+    g = dict(g, params=dict(g["params"], n=1024, delta=g["params"]["delta"] / 4))
     ch = build_channel(pa, g["params"])
     np.random.seed(int(g["seed"]))
     out = ch.run(pupil=False).get()
     want, _ = oracle_field(g, "f64")
     assert rel_l2(out, want) < 2e-5
-    assert rel_l2(out, g["field"]) < 5e-3
 
 
 def test_full_size_tc_vs_complex128():
