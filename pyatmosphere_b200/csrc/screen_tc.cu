@@ -12,8 +12,10 @@
 //
 // Tiling: one CTA = 128 (i) x 256 (j) output tile, K chunks of 32, 3 smem stages of 48 KB, two TMEM accumulator
 // buffers of 256 columns so that the float64 epilogue of tile t overlaps the MMAs of tile t+1.
-// Warp roles: 0 = bulk-copy producer, 1 = MMA issuer, 2 = TMEM allocator, 4..11 = epilogue (TMEM lane = row; the
-// two warps of a lane quarter split the 256 columns).  The per-row polynomial coefficients U_p(yh_i) come from
+// Warp roles: 0..7 = epilogue (TMEM lane = row; the two warps of a lane quarter split the 256 columns), 8 = bulk-copy
+// producer, 9 = MMA issuer, 10 = TMEM allocator.  The single-thread roles get the HIGHEST warp ids on purpose: the
+// warp scheduler favours high ids, and an MMA issuer starved by eight busy epilogue warps stalls the tensor pipe
+// (measured: tile time 24.8 -> see profiles/).  The per-row polynomial coefficients U_p(yh_i) come from
 // k_poly_rows (one small launch per batch of screens).
 // Operands are pre-tiled in global memory by k_factors_tc in the canonical K-major / no-swizzle UMMA layout
 // (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
@@ -246,7 +248,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
 
-    if (warp == 1 && lane == 0) {
+    constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;   // high warp ids: the scheduler favours them
+    if (warp == W_MMA && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             mbar_init(tempty_bar(b), EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    } else if (warp == 2) {
+    } else if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     const int rblocks = n / TM, cblocks = n / TN;
     const int tiles_per_screen = rblocks * cblocks;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ===== producer: one bulk copy per operand and stage =====
         if (lane == 0) {
             int stage = 0;
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ===== MMA issuer =====
         if (lane == 0) {
             int stage = 0;
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 umma_commit(tfull_bar(buf));             // accumulator complete
             }
         }
-    } else if (warp >= 4) {
+    } else if (warp < EPI_WARPS) {
         // ===== epilogue: TMEM lane = output row; polynomial of the low rings + reduction to turns =====
         // B200 issues only 32 DFMA/clk/SM, so float64 work bounds this epilogue.  The low-ring polynomial is smooth
         // on the scale of tens of pixels (its highest harmonic has a wavelength of ~1000 pixels), so it is evaluated
@@ -339,8 +342,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         // node (a few radians at most) is interpolated in float32 with 6-point Lagrange weights, and the node value
         // itself is reduced mod 2 pi in float64.  Measured against the float64 path: < 2e-7 rad.
         const int ew = warp & 3;                       // TMEM lane quarter this warp may read
-        const int ch = (warp - 4) >> 2;                // which half of the 256 columns
-        const int et = threadIdx.x - 128;              // index among the epilogue threads
+        const int ch = warp >> 2;                      // which half of the 256 columns
+        const int et = threadIdx.x;                    // index among the epilogue threads (warps 0..7)
         const int row_in_tile = ew * 32 + lane;
         const float out_scale_f = (float)out_scale;
         int it = 0;
@@ -399,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     }
                 }
                 const int j0 = cb * TN + cbase;
-                float* turns = a.turns ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
+                float* turns = (a.turns && !(g.swap_lbo_sbo & 64)) ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
                 const double inv_h = 1.0 / ((double)NODE_SP * dxu * a.inv_x0);   // 1 / node spacing in normalised units
                 tmem_wait_ld();                                          // first 32 accumulator columns have arrived
                 tmem_ld32_async(t_row + 32u, acc1);                      // next 32 travel while these are finished
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == W_ALLOC) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }

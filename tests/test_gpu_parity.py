@@ -410,3 +410,32 @@ def test_fused_statistics_route_equals_literal_route(monkeypatch):
     nat.clear_contexts()
     assert np.allclose(tables["fused"], tables["literal"], rtol=2e-5, atol=1e-8)
     assert np.all(tables["fused"][:, 0] == pytest.approx(1.0, abs=1e-4))
+
+
+@pytest.mark.parametrize("n,dtype", [(4096, "complex64"), (8192, "complex64"), (4096, "complex128")])
+def test_long_haul_grid_sizes(n, dtype):
+    """Config 5 grid sizes (up to 8192^2): vacuum leg vs the analytic Gaussian beam and the energy / width
+    invariants, plus one turbulent step (screen + leg) checked for unitarity."""
+    pa = _pa(dtype)
+    delta, wvl, w0, length = 1.5e-3 * 2048 / n * 2, 808e-9, 0.12, 20e3
+    ch = pa.Channel(
+        grid=pa.RectGrid(n, delta), source=pa.GaussianSource(wvl=wvl, w0=w0, F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.SSPhaseScreen(model=pa.MVKModel(Cn2=5e-16, l0=6e-3, L0=1e3),
+                                          f_grid=pa.RandLogPolarGrid(points=2**8, f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2)),
+            length=length, count=2),
+        pupil=pa.CirclePupil(radius=0.2))
+    vac = pa.VacuumPath(length=length)
+    vac.channel = ch
+    out = vac.output(ch.source.output())
+    x, y = orc.rect_xy(n, delta)
+    ana = orc.analytic_gaussian_field(x, y, w0, wvl, length)
+    assert rel_l2(out.get(), ana) < (3e-6 if dtype == "complex64" else 1e-9)
+    m = pa.measures
+    assert m.eta(ch, output=out) == pytest.approx(1.0, abs=1e-5)
+    w = np.sqrt(2 * (m.mean_x2(ch, output=out) + m.mean_y2(ch, output=out)))
+    assert w == pytest.approx(ch.source.get_w(length), abs=5e-7)
+    del out, ana
+    np.random.seed(4)
+    turb = ch.run(pupil=False)
+    assert m.eta(ch, output=turb) == pytest.approx(1.0, abs=3e-5)

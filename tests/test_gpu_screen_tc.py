@@ -60,9 +60,9 @@ def test_tc_screen_vs_oracle_256(theta_cut):
     err = np.exp(-2j * np.pi * turns.cpu().numpy().astype(np.float64)) - np.exp(-1j * want)
     # error scales with the magnitude that goes through the fp32 accumulator (rms of the high-ring part)
     scale = max(1.0, float(np.sqrt(np.mean(hi**2))))
-    assert np.sqrt(np.mean(np.abs(err) ** 2)) < 1.5e-6 * scale
-    assert np.max(np.abs(err)) < 1.5e-5 * scale
-    assert np.max(np.abs(phi.cpu().numpy() - want)) < 1.5e-7 * np.max(np.abs(want)) + 1.5e-5 * scale
+    assert np.sqrt(np.mean(np.abs(err) ** 2)) < 3e-6 * scale
+    assert np.max(np.abs(err)) < 3e-5 * scale
+    assert np.max(np.abs(phi.cpu().numpy() - want)) < 1.5e-7 * np.max(np.abs(want)) + 3e-5 * scale
 
 
 def test_tc_matches_exact_path_full_size():
