@@ -381,7 +381,7 @@ static void source_params(double w0, double wvl, double F0, double* amp, double*
 
 static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coef, int m, int m_split, int degree,
                    double shift_x, double shift_y, int nscreens, void* turns, void* phi, int phi_f64, int method,
-                   double coef_bound, cudaStream_t st) {
+                   double coef_bound, cudaStream_t st, int tc_phase = 2, int tc_first = 0, int tc_total = -1) {
     PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called before generating screens");
     PA_REQUIRE(m > 0 && m_split >= 0 && m_split <= m, "bad m / m_split (%d, %d)", m, m_split);
     PA_REQUIRE(degree >= -1 && degree <= kMaxPolyDegree, "polynomial degree %d outside [-1, %d]", degree, kMaxPolyDegree);
@@ -431,13 +431,16 @@ static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coe
         int e = 15 - (int)ceil(log2(bound));
         e = e < 0 ? 0 : (e > 10 ? 10 : e);
         a.p_scale = ldexp(1.0, e);
-        const size_t need = screen_tc_workspace(n, m, m_split, nscreens);
+        const size_t need = screen_tc_workspace(n, m, m_split, tc_total > 0 ? tc_total : nscreens);
         PA_REQUIRE(c->tcws_bytes >= need, "tensor-core screen workspace not reserved");
-        int rc = launch_screen_poly(a, st);
-        if (rc) return check_launch(rc, "screen polynomial");
+        if (tc_phase != 1) {            // polynomial coefficients belong to the preparation phase
+            int rc = launch_screen_poly(a, st);
+            if (rc) return check_launch(rc, "screen polynomial");
+        }
         static const int swap = getenv("PYATM_TC_SWAP") ? atoi(getenv("PYATM_TC_SWAP")) : 0;
-        note(3);
-        return check_launch(launch_screen_tc(a, c->tcws, c->tc_err, c->num_sms, swap, st), "tensor-core screen synthesis");
+        note(tc_phase == 1 ? 1 : (tc_phase == 0 ? 3 : 4));
+        return check_launch(launch_screen_tc(a, c->tcws, c->tc_err, c->num_sms, swap, st, tc_phase, tc_first, tc_total),
+                            "tensor-core screen synthesis");
     }
     note(3);
     return check_launch(launch_screen_exact(a, st), "screen synthesis");
@@ -696,8 +699,11 @@ static int propagate_impl(pa_ctx* c, const pa_path* p, void* field, int batch, c
     cudaStream_t st = (cudaStream_t)stream;
     const int S = p->n_screens, n = c->n;
     int rc;
+    const bool tc_hoist = S > 0 && p->screen_method == PA_SCREEN_TC;
     if (S > 0) {
-        rc = ensure_screen_ws(c, batch, p->m, p->m_split, p->degree, p->screen_method);
+        // tensor-core method: operands and polynomial tables of ALL S x batch screens are prepared by three launches up
+        // front (the coefficients of every path position are known), the per-position work is the contraction alone
+        rc = ensure_screen_ws(c, tc_hoist ? S * batch : batch, p->m, p->m_split, p->degree, p->screen_method);
         if (rc) return rc;
         rc = grow(&c->turns, &c->turns_bytes, (size_t)batch * n * n * c->rsize());
         if (rc) return rc;
@@ -720,8 +726,16 @@ static int propagate_impl(pa_ctx* c, const pa_path* p, void* field, int batch, c
         perm = want_perm_out;
         return r;
     };
+    if (tc_hoist) {
+        rc = screens(c, fx, fy, coef, p->m, p->m_split, p->degree, p->shift_x, p->shift_y, S * batch, nullptr, nullptr, 0,
+                     p->screen_method, p->coef_bound, st, 0, 0, S * batch);
+        if (rc) return rc;
+    }
     auto gen_screen = [&](int i) -> int {   // coefficient arrays are [S][batch][m]: one contiguous slab per path position
         const size_t o = (size_t)i * batch * p->m;
+        if (tc_hoist)
+            return screens(c, fx + o, fy + o, coef + 2 * o, p->m, p->m_split, p->degree, p->shift_x, p->shift_y, batch, c->turns,
+                           nullptr, 0, p->screen_method, p->coef_bound, st, 1, i * batch, S * batch);
         return screens(c, fx + o, fy + o, coef + 2 * o, p->m, p->m_split, p->degree, p->shift_x, p->shift_y, batch, c->turns,
                        nullptr, 0, p->screen_method, p->coef_bound, st);
     };

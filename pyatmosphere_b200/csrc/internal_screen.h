@@ -33,6 +33,7 @@ int screen_init_constants();
 int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st);
 int launch_screen_poly(const ScreenLaunch& a, cudaStream_t st);
 size_t screen_tc_workspace(int n, int m, int m_split, int nscreens);
-int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st);
+int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st, int phase = 2,
+                     int first_screen = 0, int total_screens = -1);
 
 }  // namespace pa

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
 
 // ---- per-row polynomial coefficients: U[s][p][i] = sum_{q <= D-p} T_pq yh_i^q ---------------------------------
 // grid: (n/128, D+1, nscreens), block 128: one (row, p) per thread.
-__global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U) {
+__global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U, size_t u_stride) {
     const int D = a.degree;
     const int i = blockIdx.x * 128 + threadIdx.x;
     const int p = blockIdx.y;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U) {
         if ((q & 1) == 0) u0 = fma(u0, y2, __ldg(tcf + q));
         else u1 = fma(u1, y2, __ldg(tcf + q));
     }
-    U[((size_t)s * (D + 1) + p) * a.n + i] = fma(u1, yh, u0);
+    U[(size_t)s * u_stride + (size_t)p * a.n + i] = fma(u1, yh, u0);
 }
 
 // 6-point Lagrange weights for nodes -2..3 at s = r/16 (sum to one; applied to differences from node 0)
@@ -226,7 +226,8 @@ struct TcArgs {
     int total_tiles;    // nscreens * (n/128) * (n/256)
     int swap_lbo_sbo;   // debug bits: 1 = swap LBO/SBO, 2 = no bulk copies, 4 = no MMAs, 8 = no epilogue math (timing experiments)
     int* err;
-    const double* U;    // [nscreens][degree+1][n]: U_p(yh_i) = sum_q T_pq yh_i^q
+    const double* U;    // [nscreens][u_stride]: U_p(yh_i) = sum_q T_pq yh_i^q at [p * n + i]
+    size_t u_stride;
 };
 
 __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
             const int rb = rem / cblocks, cb = rem % cblocks;
             const int i = rb * TM + row_in_tile;
-            const double* U = g.U + (size_t)s * (D + 1) * n + i;       // U[p * n]: coalesced over the lanes of a warp
+            const double* U = g.U + (size_t)s * g.u_stride + i;        // U[p * n]: coalesced over the lanes of a warp
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");     // previous tile's readers are done
             for (int p = ch; p <= D; p += 2) sU[p * TM + row_in_tile] = __ldg(U + (size_t)p * n);
             // Column coordinates.  The reference's axis is float32 (x_j = fl32(j * delta) + shift), i.e. a uniform
@@ -471,20 +472,34 @@ size_t screen_tc_workspace(int n, int m, int m_split, int nscreens) {
            (size_t)nscreens * (kMaxPolyDegree + 1) * n * sizeof(double);      // + U table
 }
 
-int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st) {
+// phase: 0 = prepare only (operands + row coefficients for the a.nscreens screens of `a`, stored as screens
+// [first_screen, first_screen + a.nscreens) of a workspace laid out for total_screens); 1 = contraction only for those
+// screens (their operands must have been prepared); 2 = both.
+int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st, int phase,
+                     int first_screen, int total_screens) {
     using namespace tc;
     if (a.n % TN != 0) return (int)cudaErrorInvalidValue;
     const int nhigh = a.m - a.m_split;
     int kpad = ((2 * nhigh + BK - 1) / BK) * BK;
     if (kpad == 0) kpad = BK;
-    __half* P = (__half*)workspace;
-    __half* Q = P + (size_t)a.nscreens * 2 * a.n * kpad;
-    double* U = reinterpret_cast<double*>(Q + (size_t)a.nscreens * 2 * a.n * kpad);
-    dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
-    k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
-    if (a.degree >= 0) {
-        dim3 gu(a.n / 128, a.degree + 1, a.nscreens);
-        k_poly_rows<<<gu, 128, 0, st>>>(a, U);
+    if (total_screens < 0) total_screens = a.nscreens;
+    const size_t pq_stride = (size_t)2 * a.n * kpad;                    // halves per screen (hi + lo)
+    const size_t u_stride = (size_t)(kMaxPolyDegree + 1) * a.n;        // doubles reserved per screen
+    __half* Pall = (__half*)workspace;
+    __half* Qall = Pall + (size_t)total_screens * pq_stride;
+    double* Uall = reinterpret_cast<double*>(Qall + (size_t)total_screens * pq_stride);
+    __half* P = Pall + (size_t)first_screen * pq_stride;
+    __half* Q = Qall + (size_t)first_screen * pq_stride;
+    // row coefficients are packed with the actual degree: [(D+1)][n] per screen inside the reserved slab
+    double* U = Uall + (size_t)first_screen * u_stride;
+    if (phase == 0 || phase == 2) {
+        dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
+        k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
+        if (a.degree >= 0) {
+            dim3 gu(a.n / 128, a.degree + 1, a.nscreens);
+            k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride);
+        }
+        if (phase == 0) return (int)cudaGetLastError();
     }
     static bool attr_done = false;
     if (!attr_done) {
@@ -501,6 +516,7 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     g.swap_lbo_sbo = swap;
     g.err = err_flag;
     g.U = U;
+    g.u_stride = u_stride;
     const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
     k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
     return (int)cudaGetLastError();
