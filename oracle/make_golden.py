@@ -146,6 +146,28 @@ def case_simulation(pa, p, seed, count):
                         stats=stats, versions=_versions(), **params_arrays(p))
 
 
+def case_time_series(pa, p, seed, count, times):
+    """Frozen-flow records: TimeBWcorrSimulation (mean_x, mean_y per time lag), TimeCoherenceResult (eta behind the
+    channel's pupil per time lag) and SIResult-style on-axis intensity per leg, from the reference's Simulation loop."""
+    ch = build_channel(pa, p)
+    bw = pa.simulations.TimeBWcorrSimulation(ch, times, max_size=count)
+    tc = pa.simulations.TimeCoherenceResult(ch, times, max_size=count)
+    sim = pa.simulations.Simulation([bw, tc])
+    np.random.seed(seed)
+    sim.run()
+    # on-axis intensity per leg (SIResult's record) in a simulation of its own: mixing it with time-lag records runs into
+    # the reference's broken cached-screen branch (phase_screens.py:117-121)
+    ch2 = build_channel(pa, p)
+    si = pa.simulations.Measure(ch2, "propagation", pa.simulations.si.intensity_at_center, name="i0", max_size=count)
+    sim2 = pa.simulations.Simulation([], [si])
+    np.random.seed(seed)
+    sim2.run()
+    np.savez_compressed(os.path.join(OUT, "timeseries128.npz"), seed=seed, times=np.array(times),
+                        mean_x=np.array(bw.measures[0].data, dtype=np.float64), mean_y=np.array(bw.measures[1].data, dtype=np.float64),
+                        eta=np.array(tc.measures[0].data, dtype=np.float64), i0=np.array(si.data, dtype=np.float64),
+                        versions=_versions(), **params_arrays(p))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     pa = _import_reference()
@@ -162,6 +184,7 @@ def main():
                  f_min=1 / 1e3 / 15, f_max=1 / 3e-3 * 2, length=10e3, count=5, pupil=0.12)
     case_turbulent(pa, "quick256", quick, seed=5, with_legs=False)
     case_simulation(pa, small, seed=2024, count=6)
+    case_time_series(pa, small, seed=77, count=3, times=(0.0, 0.012, 0.05))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

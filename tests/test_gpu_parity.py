@@ -443,3 +443,31 @@ def test_long_haul_grid_sizes(n, dtype):
     np.random.seed(4)
     turb = ch.run(pupil=False)
     assert m.eta(ch, output=turb) == pytest.approx(1.0, abs=3e-5)
+
+
+def test_time_series_and_si_records_match_reference():
+    """§8f n2/n3: TimeBWcorrSimulation + TimeCoherenceResult (frozen flow, shift=(0,t), wind=True) and SIResult through
+    the generic Simulation route reproduce the reference's records for the same seed."""
+    g = load_golden("timeseries128")
+    p = g["params"]
+    pa = _pa("complex64", rng="numpy")
+    times = tuple(float(t) for t in g["times"])
+    count = g["mean_x"].shape[0]
+    ch = build_channel(pa, p)
+    bw = pa.simulations.TimeBWcorrSimulation(ch, times, max_size=count)
+    tc = pa.simulations.TimeCoherenceResult(ch, times, max_size=count)
+    sim = pa.simulations.Simulation([bw, tc])
+    assert not sim.batchable()
+    np.random.seed(int(g["seed"]))
+    sim.run()
+    # vs the reference's complex64 run: limited by the reference's own screen error (5e-3 rel on the field)
+    assert np.allclose(np.asarray(bw.measures[0]), g["mean_x"], rtol=2e-2, atol=3e-5)
+    assert np.allclose(np.asarray(bw.measures[1]), g["mean_y"], rtol=2e-2, atol=3e-5)
+    assert np.allclose(np.asarray(tc.measures[0]), g["eta"], rtol=2e-3)
+    assert len(bw.xx) == len(times) and len(tc.tc) == len(times) and tc.tc[0] == pytest.approx(1.0)
+    ch2 = build_channel(pa, p)
+    si = pa.simulations.SIResult(ch2, max_size=count)
+    np.random.seed(int(g["seed"]))
+    pa.simulations.Simulation([si]).run()
+    assert np.allclose(si.intensities_at_center, g["i0"], rtol=2e-2)
+    assert si.si.shape == (p["count"] + 1,) and np.allclose(si.positions[-1], p["length"])

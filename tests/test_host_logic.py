@@ -49,7 +49,8 @@ def test_public_names_match_reference_surface():
         assert hasattr(pa, name), name
     for name in ["I", "eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2"]:
         assert callable(getattr(pa.measures, name))
-    for name in ["Simulation", "Measure", "Result", "BeamResult", "PDTResult", "TrackedPDTResult"]:
+    for name in ["Simulation", "Measure", "Result", "BeamResult", "PDTResult", "TrackedPDTResult", "SIResult", "WindResult",
+                 "TimeCoherenceResult", "TimeBWcorrSimulation"]:
         assert hasattr(pa.simulations, name)
     assert "use_gpu" in pa.gpu.config and callable(pa.gpu.get_array) and callable(pa.gpu.get_xp)
 

@@ -180,3 +180,41 @@ def test_positions_and_legs():
 def test_histogram_convention():
     h = orc.pdt_histogram([0.0, 0.004999, 0.005, 1.0, 1.2, -0.1, 0.9999], bins=200)
     assert h.sum() == 5 and h[0] == 2 and h[1] == 1 and h[199] == 2
+
+
+def test_time_series_replay():
+    """Frozen-flow records of the reference (TimeBWcorrSimulation, TimeCoherenceResult) and the per-leg on-axis
+    intensity (SIResult's record): one spectrum per screen and iteration, re-evaluated with shift=(0, t)
+    (simulations/simulation.py:94-109, phase_screens.py:93-116, simulations/wind.py, simulations/si.py:11-12)."""
+    g = load_golden("timeseries128")
+    p = g["params"]
+    x, y = _axes(p)
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    psd = orc.ring_psd(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+    pos = orc.screen_positions(p["length"], p["count"])
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="ref")
+    np.random.seed(int(g["seed"]))
+    for it in range(g["mean_x"].shape[0]):
+        spectra = [orc.draw_spectrum(base, psd) for _ in range(p["count"])]
+        for ti, t in enumerate(g["times"]):
+            screens = []
+            for rho, theta, value in spectra:
+                fx, fy = orc.spectrum_to_fxy(rho, theta)
+                screens.append(orc.ss_screen(x, y, fx, fy, value, shift=(0, t), mode="ref"))
+            out = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", through_output=False)
+            m = orc.moments(out, x, y, p["delta"], pupils=[(p["pupil"], (0, 0))], mode="ref")
+            assert m["mean_x"] == pytest.approx(g["mean_x"][it, ti], rel=2e-5, abs=1e-8)
+            assert m["mean_y"] == pytest.approx(g["mean_y"][it, ti], rel=2e-5, abs=1e-8)
+            assert m["eta_pupil"][0] == pytest.approx(g["eta"][it, ti], rel=2e-5)
+    # on-axis intensity after every screen and at the end (separate simulation, same seed)
+    np.random.seed(int(g["seed"]))
+    c = p["n"] // 2
+    for it in range(g["i0"].shape[0]):
+        screens = []
+        for _ in range(p["count"]):
+            rho, theta, value = orc.draw_spectrum(base, psd)
+            fx, fy = orc.spectrum_to_fxy(rho, theta)
+            screens.append(orc.ss_screen(x, y, fx, fy, value, mode="ref"))
+        out, legs = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", keep_legs=True, through_output=False)
+        got = [abs(u[c, c]) ** 2 for u in legs] + [abs(out[c, c]) ** 2]
+        assert np.allclose(got, g["i0"][it], rtol=2e-5)
