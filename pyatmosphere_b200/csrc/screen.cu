@@ -55,50 +55,81 @@ __global__ void k_screen_factors64(ScreenLaunch a) {
 }
 
 // ---- polynomial coefficients of the low rings -----------------------------------------------------------
-// T^_pq = Re( i^(p+q) sum_{m<m_split} c_m (2 pi fx_m X0)^p (2 pi fy_m Y0)^q ) / (p! q!)
-// grid: ((D+1)^2, nscreens), block 128.  Entries with p+q > D are written as 0.
-__global__ void k_screen_poly_coef(ScreenLaunch a) {
-    const int D = a.degree;
-    const int p = blockIdx.x / (D + 1);
-    const int q = blockIdx.x % (D + 1);
-    const int s = blockIdx.y;
-    double* out = a.polyc + (size_t)s * (D + 1) * (D + 1) + blockIdx.x;
-    if (p + q > D) {
-        if (threadIdx.x == 0) *out = 0.0;
-        return;
+// T^_pq = Re( i^(p+q) sum_{m<m_split} c_m (2 pi fx_m X0)^p (2 pi fy_m Y0)^q ) / (p! q!),   p + q <= D
+// grid: (nscreens, kPolySplit), block 256.  Rings are processed in chunks of 32: their power tables a^p, b^q
+// (p, q <= D) are built once per chunk in shared memory, then every thread accumulates its (p,q) pairs with one
+// DMUL + two DFMA per ring (the float64 pipe is the bound: 32 lanes/clk/SM on B200).  Entries with p+q > D are 0.
+constexpr int kPolySplit = 4;
+constexpr int kPolyChunk = 32;
+__global__ void __launch_bounds__(256) k_screen_poly_coef(ScreenLaunch a) {
+    const int D = a.degree, D1 = D + 1;
+    const int s = blockIdx.x;
+    __shared__ double apow[kPolyChunk][kMaxPolyDegree + 1];
+    __shared__ double bpow[kPolyChunk][kMaxPolyDegree + 1];
+    __shared__ double cre[kPolyChunk], cim[kPolyChunk];
+    // pairs handled by this block: index e = p * D1 + q with e % kPolySplit == blockIdx.y, up to 4 per thread
+    constexpr int kPer = ((kMaxPolyDegree + 1) * (kMaxPolyDegree + 1) + 256 * kPolySplit - 1) / (256 * kPolySplit);
+    double sr[kPer], si[kPer];
+    int pe[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        sr[u] = 0.0;
+        si[u] = 0.0;
+        const int e = (threadIdx.x + 256 * u) * kPolySplit + blockIdx.y;
+        pe[u] = (e < D1 * D1 && (e / D1 + e % D1) <= D) ? e : -1;
     }
-    double sr = 0.0, si = 0.0;
-    for (int m = threadIdx.x; m < a.m_split; m += blockDim.x) {
-        const double fa = 6.283185307179586476925287 * (double)a.fx[(size_t)s * a.m + m] * a.x0;
-        const double fb = 6.283185307179586476925287 * (double)a.fy[(size_t)s * a.m + m] * a.y0;
-        double w = 1.0;
-        for (int u = 0; u < p; ++u) w *= fa;
-        for (int u = 0; u < q; ++u) w *= fb;
-        const float2 c = a.coef[(size_t)s * a.m + m];
-        sr += (double)c.x * w;
-        si += (double)c.y * w;
-    }
-    __shared__ double red[2][4];
-    for (int o = 16; o > 0; o >>= 1) {
-        sr += __shfl_xor_sync(0xffffffffu, sr, o);
-        si += __shfl_xor_sync(0xffffffffu, si, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        red[0][threadIdx.x >> 5] = sr;
-        red[1][threadIdx.x >> 5] = si;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        sr = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-        si = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-        double v;
-        switch ((p + q) & 3) {   // Re(i^k (sr + i si))
-            case 0: v = sr; break;
-            case 1: v = -si; break;
-            case 2: v = -sr; break;
-            default: v = si; break;
+    for (int m0 = 0; m0 < a.m_split; m0 += kPolyChunk) {
+        __syncthreads();
+        if (threadIdx.x < 2 * kPolyChunk) {          // one thread per (ring, a-or-b) builds a power table
+            const int r = threadIdx.x >> 1, which = threadIdx.x & 1, m = m0 + r;
+            double base = 0.0;
+            if (m < a.m_split)
+                base = 6.283185307179586476925287 * (which ? (double)a.fy[(size_t)s * a.m + m] * a.y0 : (double)a.fx[(size_t)s * a.m + m] * a.x0);
+            double w = 1.0;
+            double* row = which ? bpow[r] : apow[r];
+            for (int p = 0; p <= D; ++p) {
+                row[p] = w;
+                w *= base;
+            }
+            if (!which) {
+                const float2 c = m < a.m_split ? a.coef[(size_t)s * a.m + m] : make_float2(0.f, 0.f);
+                cre[r] = (double)c.x;
+                cim[r] = (double)c.y;
+            }
         }
-        *out = v * c_invfact[p] * c_invfact[q];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < kPer; ++u) {
+            if (pe[u] < 0) continue;
+            const int p = pe[u] / D1, q = pe[u] % D1;
+            double tr = sr[u], ti = si[u];
+#pragma unroll 4
+            for (int r = 0; r < kPolyChunk; ++r) {
+                const double w = apow[r][p] * bpow[r][q];
+                tr = fma(cre[r], w, tr);
+                ti = fma(cim[r], w, ti);
+            }
+            sr[u] = tr;
+            si[u] = ti;
+        }
+    }
+    double* out = a.polyc + (size_t)s * D1 * D1;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u) {
+        const int e = (threadIdx.x + 256 * u) * kPolySplit + blockIdx.y;
+        if (e >= D1 * D1) continue;
+        double v = 0.0;
+        if (pe[u] >= 0) {
+            const int p = e / D1, q = e % D1;
+            switch ((p + q) & 3) {   // Re(i^k (sr + i si))
+                case 0: v = sr[u]; break;
+                case 1: v = -si[u]; break;
+                case 2: v = -sr[u]; break;
+                default: v = si[u]; break;
+            }
+            v *= c_invfact[p] * c_invfact[q];
+        }
+        out[e] = v;
     }
 }
 
@@ -205,8 +236,8 @@ __global__ void __launch_bounds__(256) k_screen_gemm64(ScreenLaunch a) {
 
 int launch_screen_poly(const ScreenLaunch& a, cudaStream_t st) {
     if (a.degree >= 0) {
-        dim3 g((a.degree + 1) * (a.degree + 1), a.nscreens);
-        k_screen_poly_coef<<<g, 128, 0, st>>>(a);
+        dim3 g(a.nscreens, kPolySplit);
+        k_screen_poly_coef<<<g, 256, 0, st>>>(a);
     }
     return (int)cudaGetLastError();
 }
@@ -218,8 +249,8 @@ int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st) {
         k_screen_factors64<<<g, 256, 0, st>>>(a);
     }
     if (a.degree >= 0) {
-        dim3 g((a.degree + 1) * (a.degree + 1), a.nscreens);
-        k_screen_poly_coef<<<g, 128, 0, st>>>(a);
+        dim3 g(a.nscreens, kPolySplit);
+        k_screen_poly_coef<<<g, 256, 0, st>>>(a);
     }
     const int smem_gemm = 4 * kKC * kTS * (int)sizeof(double);
     const int smem_poly = (a.degree + 1) * kTS * (int)sizeof(double);

@@ -471,3 +471,24 @@ def test_time_series_and_si_records_match_reference():
     pa.simulations.Simulation([si]).run()
     assert np.allclose(si.intensities_at_center, g["i0"], rtol=2e-2)
     assert si.si.shape == (p["count"] + 1,) and np.allclose(si.positions[-1], p["length"])
+
+
+def test_simulation_sharded_over_two_gpus_matches_single_process(tmp_path):
+    """§8e: realizations sharded over ranks (NCCL), records gathered on every rank == single-process records."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from conftest import ROOT
+    import os
+    outs = {}
+    for world in (1, 2):
+        out = str(tmp_path / f"rec{world}.npy")
+        env = dict(os.environ, PYATM_NCCL_OUT=out)
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                            "--master-addr", "127.0.0.1", "--master-port", str(29520 + world),
+                            os.path.join(ROOT, "tests", "_nccl_sim_worker.py")], env=env, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+        outs[world] = np.load(out)
+    assert np.array_equal(outs[1], outs[2])
