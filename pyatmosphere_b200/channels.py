@@ -52,14 +52,14 @@ class Channel:
 
 def QuickChannel(Cn2=1e-15, length=1e3, count_ps=5, beam_w0=0.09, beam_wvl=808e-9, aperture_radius=0.02,
                  grid_resolution=1024, grid_delta=0.001):
-    """channels.py:53-80: 1024^2 / 1 mm grid, collimated Gaussian, `count_ps` MVK sparse-spectrum screens
-    (l0 = 3 mm, L0 = 1 km, 2^10 rings between 1/15 km and 2/l0), circular aperture."""
+    """The reference's one-call channel (channels.py:53-80): 1024^2 grid at 1 mm, collimated Gaussian beam, `count_ps`
+    identical MVK sparse-spectrum screens (l0 = 3 mm, L0 = 1 km, 2^10 rings from 1/(15 L0) to 2/l0), circular aperture."""
+    inner_scale, outer_scale = 3e-3, 1e3
+    screen = SSPhaseScreen(
+        model=MVKModel(Cn2=Cn2, l0=inner_scale, L0=outer_scale),
+        f_grid=RandLogPolarGrid(points=2**10, f_min=1 / outer_scale / 15, f_max=1 / inner_scale * 2))
     return Channel(
         grid=RectGrid(resolution=grid_resolution, delta=grid_delta),
         source=GaussianSource(wvl=beam_wvl, w0=beam_w0, F0=np.inf),
-        path=IdenticalPhaseScreensPath(
-            phase_screen=SSPhaseScreen(
-                model=MVKModel(Cn2=Cn2, l0=3e-3, L0=1e3),
-                f_grid=RandLogPolarGrid(points=2**10, f_min=1 / 1e3 / 15, f_max=1 / 3e-3 * 2)),
-            length=length, count=count_ps),
+        path=IdenticalPhaseScreensPath(phase_screen=screen, length=length, count=count_ps),
         pupil=CirclePupil(radius=aperture_radius))

@@ -1,6 +1,8 @@
-"""Spatial and spectral grids.  Host-side float32 vectors only (a few KiB): the N x N arrays the reference
-builds from them (rho^2, f^2, masks) are never materialised here, the kernels rebuild them from the axes.
-Behavioural mirror of /root/reference/pyatmosphere/grids.py:12-119."""
+"""Spatial and spectral grids (API of /root/reference/pyatmosphere/grids.py:12-119).
+
+Only small host-side float32 vectors live here (a few KiB): the N x N arrays the reference derives from them
+(rho^2, f^2, aperture masks) are never materialised; the kernels rebuild them from the axes, which are uploaded
+once per context exactly as numpy produces them (float32 integer axis times the python-float spacing)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -20,50 +22,54 @@ class RectGrid(Grid):
 
     def __post_init__(self):
         if isinstance(self.resolution, int):
-            self.resolution = (self.resolution, self.resolution)
+            self.resolution = (self.resolution,) * 2
 
-    # ---- geometry (grids.py:23-53) ----------------------------------------------------------------------
-    @property
-    def size(self):
-        return np.array(self.resolution) * self.delta
-
-    @property
-    def shape(self):
-        return self.resolution
-
-    @property
-    def origin_index(self):
-        return (self.resolution[0] // 2, self.resolution[1] // 2)
-
+    # ---- geometry ---------------------------------------------------------------------------------------
     def _bounds(self, axis):
         n = self.resolution[axis]
         odd = bool(n % 2)
         return -n // 2 + odd, n // 2 + odd
 
     @property
+    def shape(self):
+        return self.resolution
+
+    @property
+    def size(self):
+        return self.delta * np.array(self.resolution)
+
+    @property
+    def origin_index(self):
+        nx, ny = self.resolution
+        return nx // 2, ny // 2
+
+    @property
     def extent(self):
-        (l, r), (t, b) = self._bounds(0), self._bounds(1)
-        return np.array([l, r, t, b]) * self.delta
+        return self.delta * np.array([*self._bounds(0), *self._bounds(1)])
 
-    # ---- coordinates (grids.py:55-80): float32 integer axis times the python-float spacing ---------------
-    def get_NxNy(self):
-        (l, r), (t, b) = self._bounds(0), self._bounds(1)
-        return np.ogrid[t:b, l:r]
-
-    def get_N2(self):
-        ny, nx = self.get_NxNy()
-        return ny**2 + nx**2
+    # ---- coordinates ----------------------------------------------------------------------------------------
+    def _axis(self, axis):
+        lo, hi = self._bounds(axis)
+        return np.arange(lo, hi, dtype=np.float32)
 
     def get_x(self):
-        l, r = self._bounds(0)
-        return np.arange(l, r, dtype=np.float32).reshape((1, -1)) * self.delta
+        """(1, N) row, float32."""
+        return self._axis(0)[np.newaxis, :] * self.delta
 
     def get_y(self):
-        t, b = self._bounds(1)
-        return np.arange(t, b, dtype=np.float32).reshape((-1, 1)) * self.delta
+        """(N, 1) column, float32."""
+        return self._axis(1)[:, np.newaxis] * self.delta
 
     def get_xy(self):
         return self.get_x(), self.get_y()
+
+    def get_NxNy(self):
+        (x0, x1), (y0, y1) = self._bounds(0), self._bounds(1)
+        return np.ogrid[y0:y1, x0:x1]
+
+    def get_N2(self):
+        rows, cols = self.get_NxNy()
+        return rows**2 + cols**2
 
     def get_rho2(self):
         x, y = self.get_xy()
@@ -73,27 +79,31 @@ class RectGrid(Grid):
         return np.sqrt(self.get_rho2())
 
     def get_f_grid(self):
-        n = int(np.min(self.resolution))
-        return RectGrid(resolution=n, delta=1 / (np.min(self.resolution) * self.delta))
+        """Reciprocal grid: same (square) resolution, spacing 1/(N delta)."""
+        n = np.min(self.resolution)
+        return RectGrid(resolution=int(n), delta=1 / (n * self.delta))
 
 
 @dataclass
 class RandLogPolarGrid(Grid):
-    """Log-spaced annuli with one random harmonic each (grids.py:88-119).  Draws come from numpy's global
-    legacy RNG in the reference's order, so `np.random.seed(s)` reproduces the reference's spectra."""
+    """Log-spaced annuli with one random harmonic each.  Draws come from numpy's global legacy RNG in the
+    reference's order, so `np.random.seed(s)` reproduces the reference's spectra."""
     points: int
     f_min: float
     f_max: float
 
     @property
     def base(self):
-        return np.exp(np.linspace(np.log(self.f_min), np.log(self.f_max), self.points, dtype=np.float32))
+        """Outer edges of the annuli, float32."""
+        log_edges = np.linspace(np.log(self.f_min), np.log(self.f_max), self.points, dtype=np.float32)
+        return np.exp(log_edges)
 
     def get_rho(self):
-        u = np.random.random(size=(1,)).astype(np.float32)      # ONE number shared by all annuli (grids.py:100)
+        """Radius inside every annulus, uniform in area, from ONE uniform number shared by all annuli."""
+        shared = np.random.random(size=(1,)).astype(np.float32)
         outer = self.base
         inner = np.insert(outer, 0, 0)[:-1]
-        return np.sqrt(inner**2 + u * (outer**2 - inner**2))
+        return np.sqrt(inner**2 + shared * (outer**2 - inner**2))
 
     def get_theta(self):
         return 2 * np.pi * np.random.random(size=(self.points,)).astype(np.float32)
@@ -105,4 +115,4 @@ class RandLogPolarGrid(Grid):
         return rho * np.sin(theta)
 
     def get_xy(self, rho, theta):
-        return self.get_x(rho, theta).reshape((1, -1)), self.get_y(rho, theta).reshape((-1, 1))
+        return self.get_x(rho, theta)[np.newaxis, :], self.get_y(rho, theta)[:, np.newaxis]

@@ -1,6 +1,7 @@
-"""On-axis scintillation index per leg.  Mirror of /root/reference/pyatmosphere/simulations/si.py:11-36
-(record + `si` statistic).  The closed-form Andrews curves the reference overlays (theory/atmosphere/si.py) are
-analytic post-processing outside this path: pass them in `theoretical_functions` if wanted."""
+"""On-axis scintillation index per leg: record and statistic of
+/root/reference/pyatmosphere/simulations/si.py:11-36.  The closed-form Andrews curves the reference overlays
+(theory/atmosphere/si.py) are analytic post-processing outside this path; pass callables in
+`theoretical_functions` to overlay them."""
 from __future__ import annotations
 
 import numpy as np
@@ -11,39 +12,44 @@ from .result import Result
 
 
 def intensity_at_center(channel, output):
-    iy, ix = channel.grid.origin_index
-    return float(np.abs(get_array(output[iy, ix])) ** 2)
+    """|u|^2 at the grid origin (one element read back from the device)."""
+    row, col = channel.grid.origin_index
+    centre = np.asarray(get_array(output[row, col]))
+    return float(centre.real**2 + centre.imag**2)
 
 
 class SIResult(Result):
     def __init__(self, channel, theoretical_functions=(), *args, **kwargs):
-        measures = [Measure(channel, "propagation", intensity_at_center)]
-        super().__init__(*args, channel=channel, measures=measures, **kwargs)
+        record = Measure(channel, "propagation", intensity_at_center)
+        super().__init__(*args, channel=channel, measures=[record], **kwargs)
         self.set_theoretical_functions(*theoretical_functions)
 
     def set_theoretical_functions(self, *theoretical_functions):
+        model, source = self.channel.path.phase_screen.model, self.channel.source
         self.theoretical_functions = theoretical_functions
-        self.theoretical_si = [f(self.positions, self.channel.path.phase_screen.model, self.channel.source)
-                               for f in theoretical_functions]
+        self.theoretical_si = [f(self.positions, model, source) for f in theoretical_functions]
+
+    @property
+    def positions(self):
+        """Screen positions followed by the end of the path: the planes at which the record is taken."""
+        return np.append(np.asarray(self.channel.path.positions, dtype=float), self.channel.path.length)
 
     @property
     def intensities_at_center(self):
         return np.asarray(self.measures[0])
 
     @property
-    def positions(self):
-        return np.array(list(self.channel.path.positions) + [self.channel.path.length])
-
-    @property
     def si(self):
-        i = self.intensities_at_center
-        return (i**2).mean(axis=0) / i.mean(axis=0) ** 2 - 1
+        """<I^2>/<I>^2 - 1 per plane."""
+        samples = self.intensities_at_center
+        mean = samples.mean(axis=0)
+        return np.mean(samples * samples, axis=0) / (mean * mean) - 1
 
     def plot_output(self):
         from matplotlib import pyplot as plt
         plt.plot(self.positions, self.si, label=r"On-axis SI $\sigma_I$, m")
-        for i, f in enumerate(self.theoretical_functions):
-            plt.plot(self.positions, self.theoretical_si[i], label=f"Theoretical on-axis SI: {f.__name__}")
+        for curve, f in zip(self.theoretical_si, self.theoretical_functions):
+            plt.plot(self.positions, curve, label=f"Theoretical on-axis SI: {f.__name__}")
         plt.plot(np.nan, np.nan, label=f"Iterations: {len(self.measures[0])}", alpha=0)
         plt.xlabel("Propagation distance z, m")
         plt.legend()
