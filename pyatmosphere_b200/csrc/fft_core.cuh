@@ -269,6 +269,20 @@ __device__ __forceinline__ void fft_inv(cplx<T> (&v)[E], int t, cplx<T>* sm, con
     }
 }
 
+// inverse split in two so that a caller can issue independent loads between the last exchange and the last stage:
+// head = stages L-1 .. 1 plus the exchange into the stage-0 distribution, tail = stage 0
+template <typename T, int N, int E, typename Addr, int S = plan_len(N, E) - 1>
+__device__ __forceinline__ void fft_inv_head(cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr, const cplx<T>* __restrict__ tw) {
+    if constexpr (S > 0) {
+        stage_inv<T, N, E, S>(v, t, tw);
+        exchange<T, N, E, S, S - 1>(v, t, sm, addr);
+        fft_inv_head<T, N, E, Addr, S - 1>(v, t, sm, addr, tw);
+    }
+}
+template <typename T, int N, int E> __device__ __forceinline__ void fft_inv_tail(cplx<T> (&v)[E], int t, const cplx<T>* __restrict__ tw) {
+    stage_inv<T, N, E, 0>(v, t, tw);
+}
+
 // host-side mirrors of the plan, used to build twiddle/permutation tables
 inline int host_plan_len(int n, int e) { return plan_len(n, e); }
 

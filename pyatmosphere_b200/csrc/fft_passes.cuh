@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
     C* ptr = a.field + (size_t)row * N;
     const RowAddr<N, E> addr{f * N};
     C v[E];
+#ifdef PA_PREFETCH_TURNS
+    T trv[E];
+#endif
 
     if constexpr (SRC) {
       if (a.sep != nullptr) {
@@ -115,7 +118,17 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
     } else if constexpr (IN_PERM) {
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = ptr[io_pos<N, E>(t, i)];      // spectrum in storage order
+#ifdef PA_PREFETCH_TURNS
+        fft_inv_head<T, N, E>(v, t, sm, addr, a.tw);
+        if (a.turns != nullptr) {          // screen values requested before the last inverse stage hides their latency
+            const T* tr = a.turns + (size_t)row * N;
+#pragma unroll
+            for (int i = 0; i < E; ++i) trv[i] = tr[reg_pos<N, E, 0>(t, i)];
+        }
+        fft_inv_tail<T, N, E>(v, t, a.tw);
+#else
         fft_inv<T, N, E>(v, t, sm, addr, a.tw);
+#endif
     } else {
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = ptr[reg_pos<N, E, 0>(t, i)];
@@ -126,7 +139,11 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
         const T* tr = a.turns + (size_t)row * N;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
+#ifdef PA_PREFETCH_TURNS
+            C e = expm2pi(IN_PERM ? trv[i] : tr[reg_pos<N, E, 0>(t, i)]);
+#else
             C e = expm2pi(tr[reg_pos<N, E, 0>(t, i)]);
+#endif
             e.x *= a.scale;
             e.y *= a.scale;
             v[i] = cmul(v[i], e);

@@ -492,3 +492,27 @@ def test_simulation_sharded_over_two_gpus_matches_single_process(tmp_path):
         assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
         outs[world] = np.load(out)
     assert np.array_equal(outs[1], outs[2])
+
+
+def test_error_paths_and_many_apertures():
+    """Status codes surface as exceptions with the library's message; more apertures than one sweep holds are chunked."""
+    pa = _pa("complex64")
+    from pyatmosphere_b200 import _native as nat
+    import torch
+    from pyatmosphere_b200.gpu import DeviceArray
+    bad = pa.Channel(grid=pa.RectGrid(100, 1e-3), source=pa.GaussianSource(wvl=808e-9, w0=0.02, F0=np.inf),
+                     path=pa.VacuumPath(length=10.0), pupil=pa.CirclePupil(radius=0.01))
+    with pytest.raises(nat.NativeError, match="power of two"):
+        bad.run()
+    with pytest.raises(ValueError):
+        pa.Channel(grid=pa.RectGrid((128, 256), 1e-3), source=pa.GaussianSource(wvl=808e-9, w0=0.02, F0=np.inf),
+                   path=pa.VacuumPath(length=10.0), pupil=pa.CirclePupil(radius=0.01)).run()
+    g = load_golden("turb128")
+    p = g["params"]
+    ch = build_channel(pa, p)
+    out = DeviceArray(torch.as_tensor(g["field"].astype(np.complex64)).cuda())
+    pupils = [(0.01 * (i + 1), (0.002 * i, -0.001 * i)) for i in range(11)]
+    got = pa.measures.all_moments(ch, out, pupils)["eta_pupil"][0]
+    x, y = orc.rect_xy(p["n"], p["delta"])
+    want = orc.moments(g["field"].astype(np.complex64), x, y, p["delta"], pupils=pupils, mode="f64")["eta_pupil"]
+    assert got.shape == (11,) and np.allclose(got, want, rtol=2e-6)
