@@ -19,12 +19,39 @@ namespace pa {
 // ---- shared-memory address maps ----------------------------------------------------------------------------
 // XOR swizzles that keep runs aligned to their own size intact and spread the strided accesses of the
 // late stages over the banks (checked with tools/bank_sim.py).
+
+// Rows (complex64, E = 16; one 128-byte bank row = 16 elements).  Stage with SIGMA = 1: register pairs move as
+// 16-byte chunks, a quarter warp needs 8 distinct chunks -> thread bits enter chunk bits 1-3.  Stages with
+// 1 < SIGMA < 16: a half warp needs 16 distinct slots -> the thread bits above SIGMA enter the free slot bits.
+// Sources are always bits above the targets, so every map is a bijection of [0, N).
 template <int N, int E> __device__ __forceinline__ int swz_row(int p) {
-    // bits 1-2 <- bits 4-5 (stage with SIGMA = 1, 16-byte chunks), bit 3 <- bit 7 (stage with SIGMA = 8)
-    return p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3);
+    if constexpr (E == 16 && N == 1024) {           // 16.16.4, SIGMA = 64, 4, 1
+        return p ^ (((p >> 6) & 3) << 2) ^ (((p >> 4) & 1) << 1);
+    } else if constexpr (E == 16 && (N == 4096 || N == 256)) {   // last radix 16, SIGMA = .., 16, 1
+        return p ^ (((p >> 4) & 7) << 1);
+    } else if constexpr (E == 16 && (N == 8192 || N == 512)) {   // .., 8, 4 with SIGMA = .., 4, 1
+        return p ^ (((p >> 5) & 3) << 2) ^ (((p >> 4) & 1) << 1);
+    } else {
+        // 2048 = 16.16.8: bits 1-2 <- bits 4-5 (SIGMA = 1, 16-byte chunks), bit 3 <- bit 7 (SIGMA = 8)
+        return p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3);
+    }
 }
+// Columns: a tile keeps TC columns interleaved, so a half warp covers 16/TC consecutive threads of one transform;
+// in the last stage (SIGMA = 1) they sit R_last positions apart -> their bits are folded onto the low bits.
 template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
-    return p ^ ((p >> 3) & 3);
+    if constexpr (E == 16) {
+        constexpr int RL = plan_radix(N, E, plan_len(N, E) - 1);
+        constexpr int W = TC >= 16 ? 0 : 4 - ilog2(TC);
+        if constexpr (W == 0) {
+            return p;
+        } else if constexpr (N == 8192 && TC == 1) {            // SIGMA = 4 stage as well: bit 6 -> bit 2
+            return p ^ ((p >> 2) & 15) ^ (((p >> 6) & 1) << 2);
+        } else {
+            return p ^ ((p >> ilog2(RL)) & ((1 << W) - 1));
+        }
+    } else {
+        return p ^ ((p >> 3) & 3);
+    }
 }
 
 template <int N, int E> struct RowAddr {

@@ -34,16 +34,33 @@ def reg_pos(n, e, radices, sig, s, t, idx):
     return (b // sg) * (sg * r) + (b % sg) + j * sg
 
 
-def swz_row(p):
-    return p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3)
-
-
-def swz_col(p):
-    return p ^ ((p >> 3) & 3)
-
-
 def ident(p):
     return p
+
+
+def swz_row_for(n):
+    """Mirror of swz_row<N, 16> in fft_passes.cuh (complex64 rows)."""
+    if n == 2048:
+        return lambda p: p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3)
+    if n == 1024:
+        return lambda p: p ^ (((p >> 6) & 3) << 2) ^ (((p >> 4) & 1) << 1)
+    if n in (4096, 256):
+        return lambda p: p ^ (((p >> 4) & 7) << 1)
+    if n in (8192, 512):
+        return lambda p: p ^ (((p >> 5) & 3) << 2) ^ (((p >> 4) & 1) << 1)
+    return lambda p: p ^ (((p >> 4) & 3) << 1)
+
+
+def swz_col_for(n, tc):
+    """Mirror of swz_col<N, 16, TC>."""
+    radices, _ = plan(n, 16)
+    rl = radices[-1].bit_length() - 1
+    w = 0 if tc >= 16 else 4 - (tc.bit_length() - 1)
+    if w == 0:
+        return ident
+    if n == 8192 and tc == 1:
+        return lambda p: p ^ ((p >> 2) & 15) ^ (((p >> 6) & 1) << 2)
+    return lambda p: p ^ ((p >> rl) & ((1 << w) - 1))
 
 
 def wavefronts(addrs_bytes, width):
@@ -62,7 +79,7 @@ def wavefronts(addrs_bytes, width):
 def analyse(n, e, mode, tc=4, elem=8, swz=None):
     radices, sig = plan(n, e)
     tpf = n // e
-    swz = swz or (swz_row if mode == "row" else swz_col)
+    swz = swz or (swz_row_for(n) if mode == "row" else swz_col_for(n, tc))
     print(f"N={n} E={e} radices={radices} sigma={sig} mode={mode} tc={tc if mode == 'col' else 1} elem={elem}B")
     L = len(radices)
     worst = 0.0
@@ -84,7 +101,13 @@ def analyse(n, e, mode, tc=4, elem=8, swz=None):
                         c, t = th % tc, th // tc
                         p = reg_pos(n, e, radices, sig, s, t % tpf, idx)
                         addrs.append((swz(p) * tc + c) * elem)
-                w, i = wavefronts(addrs, elem if elem <= 16 else 16)
+                wide = mode == "row" and sig[s] == 1 and elem == 8 and radices[s] % 2 == 0
+                if wide:            # the kernel moves register pairs (j, j+1) as one 128-bit access
+                    if idx % 2:
+                        continue
+                    w, i = wavefronts(addrs, 16)
+                else:
+                    w, i = wavefronts(addrs, elem if elem <= 16 else 16)
                 tot += w
                 ideal += i
         print(f"  stage {s} (R={radices[s]}, sigma={sig[s]}): wavefronts/ideal = {tot / ideal:.2f}")
