@@ -53,6 +53,7 @@ struct SepTable {          // Gaussian source carried through the first leg anal
 struct HTable {
     double length, wvl;
     void* dev;            // cplx<T>[n] permuted transfer-function factor
+    void* dev_y;          // the same factor in the composite order of the split column pass (null without it)
     double alpha_re, alpha_im;   // e^{ikL} / n^2
 };
 
@@ -69,6 +70,12 @@ struct pa_ctx {
     float* y = nullptr;
     void* tw = nullptr;                // twiddles
     std::vector<int> perm;             // frequency index held at storage position p
+    // split column pass (fft_split.cuh): outer radix (0 = off), inner-plan twiddles, outer twiddles, and the
+    // frequency held at row p of a column spectrum
+    int split = 0;
+    void* tw_sub = nullptr;
+    void* otw = nullptr;
+    std::vector<int> perm_y;
     std::vector<HTable> htabs;
     std::vector<SepTable> seps;
     bool sep_first_leg = true;   // complex64 only: start from the analytic first leg (exact identity, float64 1-D transform)
@@ -113,8 +120,8 @@ static int check_launch(int rc, const char* what) {
 }
 
 // ---- tables -------------------------------------------------------------------------------------------------
-template <typename T> static int build_twiddles(pa_ctx* c) {
-    const int n = c->n, e = c->e, L = plan_len(n, e);
+template <typename T> static int build_twiddles(int n, int e, void** out) {
+    const int L = plan_len(n, e);
     const int total = plan_tw_size(n, e);
     std::vector<cplx<T>> tw((size_t)(total > 0 ? total : 1));
     for (int s = 0; s + 1 < L; ++s) {
@@ -126,18 +133,31 @@ template <typename T> static int build_twiddles(pa_ctx* c) {
                 tw[(size_t)off + (size_t)(j - 1) * nb + b] = mkc<T>((T)cosl(ang), (T)sinl(ang));
             }
     }
-    PA_CUDA(cudaMalloc(&c->tw, tw.size() * sizeof(cplx<T>)));
-    PA_CUDA(cudaMemcpy(c->tw, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    PA_CUDA(cudaMalloc(out, tw.size() * sizeof(cplx<T>)));
+    PA_CUDA(cudaMemcpy(*out, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
+    return PA_OK;
+}
+// outer-stage twiddles of the split column transform: otw[t * R0 + j] = exp(-2 pi i t j / n), t < n / R0
+template <typename T> static int build_outer_twiddles(int n, int r0, void** out) {
+    const int m = n / r0;
+    std::vector<cplx<T>> tw((size_t)n);
+    for (int t = 0; t < m; ++t)
+        for (int j = 0; j < r0; ++j) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)((long long)t * j) / (long double)n;
+            tw[(size_t)t * r0 + j] = mkc<T>((T)cosl(ang), (T)sinl(ang));
+        }
+    PA_CUDA(cudaMalloc(out, tw.size() * sizeof(cplx<T>)));
+    PA_CUDA(cudaMemcpy(*out, tw.data(), tw.size() * sizeof(cplx<T>), cudaMemcpyHostToDevice));
     return PA_OK;
 }
 
 // perm[q] = frequency (numpy fft index) stored at index q of a spectrum.  Register idx of thread t holds, after
 // the last forward stage, position p = base_{L-1}(t, g) + j (idx = g R + j), whose frequency is the mixed-radix
 // digit reversal of p; it is stored at q = t + idx * (n/e)  (fft_core.cuh: io_pos).
-static void build_perm(pa_ctx* c) {
-    const int n = c->n, e = c->e, L = plan_len(n, e), tpf = n / e;
+static std::vector<int> storage_perm(int n, int e) {
+    const int L = plan_len(n, e), tpf = n / e;
     const int RL = plan_radix(n, e, L - 1), SL = plan_sigma(n, e, L - 1);
-    c->perm.assign(n, -1);
+    std::vector<int> perm((size_t)n, -1);
     for (int t = 0; t < tpf; ++t)
         for (int idx = 0; idx < e; ++idx) {
             const int g = idx / RL, j = idx % RL;
@@ -149,8 +169,21 @@ static void build_perm(pa_ctx* c) {
                 k += ((p / sigma) % R) * mult;
                 mult *= R;
             }
-            c->perm[t + idx * tpf] = k;
+            perm[t + idx * tpf] = k;
         }
+    return perm;
+}
+// Column spectra: the same order as rows, or - with the split pass - block j of n/R0 rows holds the frequencies
+// j + R0 * q, q in the storage order of the (n/R0)-point plan.
+static void build_perm(pa_ctx* c) {
+    c->perm = storage_perm(c->n, c->e);
+    c->perm_y = c->perm;
+    if (c->split) {
+        const int r0 = c->split, m = c->n / r0;
+        const std::vector<int> inner = storage_perm(m, c->e);
+        for (int j = 0; j < r0; ++j)
+            for (int q = 0; q < m; ++q) c->perm_y[(size_t)j * m + q] = j + r0 * inner[q];
+    }
 }
 
 // Transfer function of one leg, separable and in permuted order:
@@ -171,28 +204,33 @@ static int get_htable(pa_ctx* c, double length, double wvl, const HTable** out) 
     h.length = length;
     h.wvl = wvl;
     h.dev = nullptr;
+    h.dev_y = nullptr;
     const double ang = k * length;
     const double inv_n2 = 1.0 / ((double)n * (double)n);
     h.alpha_re = cos(ang) * inv_n2;
     h.alpha_im = sin(ang) * inv_n2;
-    std::vector<double> re(n), im(n);
-    for (int p = 0; p < n; ++p) {
-        const int q = c->perm[p];
-        const int qs = q < n / 2 ? q : q - n;
-        const double f = (double)(float)qs * df;
-        const double ph = -(coef * (f * f));
-        re[p] = cos(ph);
-        im[p] = sin(ph);
-    }
-    PA_CUDA(cudaMalloc(&h.dev, (size_t)n * c->csize()));
-    if (c->prec == 0) {
-        std::vector<float2> t(n);
-        for (int p = 0; p < n; ++p) t[p] = make_float2((float)re[p], (float)im[p]);
-        PA_CUDA(cudaMemcpy(h.dev, t.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
-    } else {
-        std::vector<double2> t(n);
-        for (int p = 0; p < n; ++p) t[p] = make_double2(re[p], im[p]);
-        PA_CUDA(cudaMemcpy(h.dev, t.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+    for (int pass = 0; pass < (c->split ? 2 : 1); ++pass) {
+        const std::vector<int>& perm = pass == 0 ? c->perm : c->perm_y;
+        void** dst = pass == 0 ? &h.dev : &h.dev_y;
+        std::vector<double> re(n), im(n);
+        for (int p = 0; p < n; ++p) {
+            const int q = perm[p];
+            const int qs = q < n / 2 ? q : q - n;
+            const double f = (double)(float)qs * df;
+            const double ph = -(coef * (f * f));
+            re[p] = cos(ph);
+            im[p] = sin(ph);
+        }
+        PA_CUDA(cudaMalloc(dst, (size_t)n * c->csize()));
+        if (c->prec == 0) {
+            std::vector<float2> t(n);
+            for (int p = 0; p < n; ++p) t[p] = make_float2((float)re[p], (float)im[p]);
+            PA_CUDA(cudaMemcpy(*dst, t.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice));
+        } else {
+            std::vector<double2> t(n);
+            for (int p = 0; p < n; ++p) t[p] = make_double2(re[p], im[p]);
+            PA_CUDA(cudaMemcpy(*dst, t.data(), (size_t)n * sizeof(double2), cudaMemcpyHostToDevice));
+        }
     }
     c->htabs.push_back(h);
     *out = &c->htabs.back();
@@ -215,8 +253,9 @@ static int get_tensor_map(pa_ctx* c, void* field, int batch, const CUtensorMap**
     }
     const int n = c->n;
     const size_t csz = c->csize();
-    const int tc = fft_tma_cols_per_tile(c->prec, n);
-    const int boxr = n < 256 ? n : 256;
+    const int tc = c->split ? fft_split_cols_per_tile(c->prec, n) : fft_tma_cols_per_tile(c->prec, n);
+    const int rows_per_tile = c->split ? n / c->split : n;
+    const int boxr = rows_per_tile < 256 ? rows_per_tile : 256;
     TensorMapEntry e;
     e.field = field;
     e.batch = batch;
@@ -363,11 +402,17 @@ static int cols(pa_ctx* c, void* field, int batch, double length, double wvl, cu
     cl.batch = batch;
     cl.tmap = nullptr;
     cl.num_sms = c->num_sms;
-    if (c->use_tma && fft_tma_supported(c->prec, c->n)) {
+    if (c->split || (c->use_tma && fft_tma_supported(c->prec, c->n))) {
         const CUtensorMap* tm = nullptr;
         rc = get_tensor_map(c, field, batch, &tm);
         if (rc) return rc;
         cl.tmap = tm;
+    }
+    if (c->split) {
+        cl.hpy = h->dev_y;
+        cl.tw_sub = c->tw_sub;
+        cl.otw = c->otw;
+        note(2);
     }
     note(1);
     return check_launch(launch_cols(c->prec, c->n, cl, st), "column pass");
@@ -498,10 +543,16 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     c->n = n;
     c->prec = precision;
     c->e = elems_per_thread(precision);
+    const bool direct = getenv("PYATM_FFT_DIRECT") && atoi(getenv("PYATM_FFT_DIRECT")) != 0;
+    c->split = direct ? 0 : fft_split_radix(precision, n);
     build_perm(c);
-    int rc = precision == 0 ? build_twiddles<float>(c) : build_twiddles<double>(c);
+    int rc = precision == 0 ? build_twiddles<float>(n, c->e, &c->tw) : build_twiddles<double>(n, c->e, &c->tw);
+    if (!rc && c->split) {
+        rc = precision == 0 ? build_twiddles<float>(n / c->split, c->e, &c->tw_sub) : build_twiddles<double>(n / c->split, c->e, &c->tw_sub);
+        if (!rc) rc = precision == 0 ? build_outer_twiddles<float>(n, c->split, &c->otw) : build_outer_twiddles<double>(n, c->split, &c->otw);
+    }
     if (rc) {
-        delete c;
+        pa_ctx_destroy(c);
         return rc;
     }
     rc = screen_init_constants();
@@ -513,7 +564,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     c->htabs.reserve(256);
     c->seps.reserve(64);
     c->num_sms = prop.multiProcessorCount;
-    c->use_tma = !(getenv("PYATM_FFT_DIRECT") && atoi(getenv("PYATM_FFT_DIRECT")) != 0);
+    c->use_tma = !direct;
     c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") && atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0;
     c->sep_first_leg = !(getenv("PYATM_NO_ANALYTIC_LEG") && atoi(getenv("PYATM_NO_ANALYTIC_LEG")) != 0);
     *out = c;
@@ -523,11 +574,13 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
 int pa_ctx_destroy(pa_ctx* c) {
     if (!c) return PA_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->x, c->y, c->tw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums};
+    void* ptrs[] = {c->x, c->y, c->tw, c->tw_sub, c->otw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums};
     for (void* p : ptrs)
         if (p) cudaFree(p);
-    for (auto& h : c->htabs)
+    for (auto& h : c->htabs) {
         if (h.dev) cudaFree(h.dev);
+        if (h.dev_y) cudaFree(h.dev_y);
+    }
     for (auto& t : c->seps)
         if (t.dev) cudaFree(t.dev);
     delete c;
@@ -545,8 +598,10 @@ int pa_ctx_set_axes(pa_ctx* c, const float* x_host, const float* y_host, double 
     c->hx.assign(x_host, x_host + c->n);
     c->hy.assign(y_host, y_host + c->n);
     if (c->delta != delta) {
-        for (auto& h : c->htabs)
+        for (auto& h : c->htabs) {
             if (h.dev) cudaFree(h.dev);
+            if (h.dev_y) cudaFree(h.dev_y);
+        }
         c->htabs.clear();
     }
     for (auto& t : c->seps)

@@ -43,6 +43,15 @@ int fft_tma_cols_per_tile(int prec, int n) {
         default: return 0;
     }
 }
+int fft_split_cols_per_tile(int prec, int n) {
+    switch (n) {
+#define PA_CASE(N) case N: return fft_split_tc_##N(prec);
+        PA_FFT_SIZES(PA_CASE)
+#undef PA_CASE
+        default: return 0;
+    }
+}
+int fft_split_radix(int prec, int n) { return fft_split_cols_per_tile(prec, n) > 0 ? kSplitRadix : 0; }
 void fft_geometry(int prec, int n, int* rt, int* rf, int* rs, int* ct, int* cc, int* cs) {
     int g[6] = {0, 0, 0, 0, 0, 0};
     switch (n) {

@@ -249,8 +249,12 @@ __global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
 template <typename T> struct ColArgs {
     cplx<T>* field;        // [batch][N][N] in place, row-spectrum form
     const cplx<T>* tw;
-    const cplx<T>* hp;     // transfer-function factor h[freq(q)] in spectrum storage order, N entries
+    const cplx<T>* hp;     // transfer-function factor h[freq(q)] in spectrum storage order, N entries (kx, and ky unless hpy is set)
     T alpha_re, alpha_im;  // e^{ikL} / N^2 (times any loss factor)
+    // split column pass (fft_split.cuh): the kernel transforms blocks of N rows of a field that is `ncols` wide;
+    // block b uses the ky factors hpy[(b % nsub) * N ...].  Ordinary pass: hpy = hp, ncols = N, nsub = 1.
+    const cplx<T>* hpy;
+    int ncols, nsub;
 };
 
 // One CTA = TC adjacent columns of one field, N/E threads per column; thread index = c + TC * t so that a warp

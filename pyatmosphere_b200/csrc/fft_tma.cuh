@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
     using G = TmaGeo<T, N, E>;
     constexpr int TC = G::TC, BOXR = G::BOXR;
     constexpr int kSlotBytes = G::SLOT;
-    constexpr int TILES_PER_FIELD = N / TC;
+    const int TILES_PER_FIELD = a.ncols / TC;       // tiles per block of N rows
     constexpr int BOX_BYTES = BOXR * TC * (int)sizeof(C);
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     C* slots = reinterpret_cast<C*>(smem_tma);
@@ -175,9 +175,10 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
         fft_fwd<T, N, E>(v, t, sm, addr, a.tw);
         {
             const C hx = cmul(ldg_c<T>(a.hp + col), mkc<T>(a.alpha_re, a.alpha_im));
+            const C* hy = a.hpy + ((tile / TILES_PER_FIELD) % a.nsub) * N;
 #pragma unroll
             for (int i = 0; i < E; ++i) {
-                const C h = cmul(ldg_c<T>(a.hp + io_pos<N, E>(t, i)), hx);
+                const C h = cmul(ldg_c<T>(hy + io_pos<N, E>(t, i)), hx);
                 v[i] = cmul(v[i], h);
             }
         }

@@ -40,6 +40,10 @@ struct ColLaunch {
     int batch;
     const void* tmap;     // host pointer to a CUtensorMap of the field ([batch*n][2n] reals), or null -> direct-access kernel
     int num_sms;
+    // split column pass (fft_split.cuh; set together, tmap then has the box of the inner transform's tiles)
+    const void* hpy = nullptr;      // ky factors in the composite order of the split transform
+    const void* tw_sub = nullptr;   // stage twiddles of the inner (n / 32)-point plan
+    const void* otw = nullptr;      // outer-stage twiddles exp(-2 pi i t j / n), [n / 32][32]
 };
 
 // implemented once per grid size in fft_n<N>.cu; return cudaError_t as int, or -1 for an unsupported size
@@ -48,6 +52,10 @@ int launch_cols(int prec, int n, const ColLaunch& a, cudaStream_t st);
 bool fft_size_supported(int prec, int n);
 bool fft_tma_supported(int prec, int n);
 int fft_tma_cols_per_tile(int prec, int n);
+// split column pass: outer radix (0 = this size/precision has no split variant) and columns per tile of the inner kernel
+constexpr int kSplitRadix = 32;
+int fft_split_radix(int prec, int n);
+int fft_split_cols_per_tile(int prec, int n);
 // number of CTAs / threads / smem of the two passes (reported through pa_fft_geometry for the roofline notes)
 void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_smem, int* cols_threads, int* cols_tc, int* cols_smem);
 
@@ -57,7 +65,8 @@ void fft_geometry(int prec, int n, int* rows_threads, int* rows_fpb, int* rows_s
     int launch_cols_##N(int prec, const ColLaunch& a, cudaStream_t st);              \
     void fft_geometry_##N(int prec, int* g);                                         \
     bool fft_tma_ok_##N(int prec);                                                   \
-    int fft_tma_tc_##N(int prec);
+    int fft_tma_tc_##N(int prec);                                                    \
+    int fft_split_tc_##N(int prec);
 PA_FFT_SIZES(PA_DECL)
 #undef PA_DECL
 

@@ -516,3 +516,19 @@ def test_error_paths_and_many_apertures():
     x, y = orc.rect_xy(p["n"], p["delta"])
     want = orc.moments(g["field"].astype(np.complex64), x, y, p["delta"], pupils=pupils, mode="f64")["eta_pupil"]
     assert got.shape == (11,) and np.allclose(got, want, rtol=2e-6)
+
+
+def test_split_column_pass_random_field_8192():
+    """8192^2 complex64 uses the split column pass (outer radix-32 stage + 256-point tiles, fft_split.cuh): a
+    random field through one leg against the float64 oracle, which exercises every frequency of the composite order."""
+    pa = _pa("complex64")
+    import torch
+    from pyatmosphere_b200.gpu import DeviceArray
+    n, delta, length, wvl = 8192, 1e-3, 1.2e3, 808e-9
+    rng = np.random.default_rng(8192)
+    u = rng.standard_normal((n, n), dtype=np.float32) + 1j * rng.standard_normal((n, n), dtype=np.float32)
+    ch = pa.Channel(grid=pa.RectGrid(n, delta), source=pa.GaussianSource(wvl=wvl, w0=0.05, F0=np.inf),
+                    path=pa.VacuumPath(length=length), pupil=pa.CirclePupil(radius=1.0))
+    out = ch.path.output(DeviceArray(torch.as_tensor(u).cuda())).get()
+    want = orc.vacuum_leg(u, length, wvl, delta, mode="f64")
+    assert rel_l2(out, want) < 2e-6
