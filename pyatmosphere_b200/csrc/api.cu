@@ -459,6 +459,8 @@ static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coe
     a.y0 = y0;
     a.inv_x0 = 1 / x0;
     a.inv_y0 = 1 / y0;
+    a.x_first = (double)c->hx[0] + (double)a.shift_x;
+    a.dxu = ((double)c->hx[n - 1] - (double)c->hx[0]) / (double)(n - 1);
     a.fx = fx;
     a.fy = fy;
     a.coef = (const float2*)coef;

@@ -15,11 +15,15 @@
 // Warp roles: 0..7 = epilogue (TMEM lane = row; the two warps of a lane quarter split the 256 columns), 8 = bulk-copy
 // producer, 9 = MMA issuer, 10 = TMEM allocator.  The single-thread roles get the HIGHEST warp ids on purpose: the
 // warp scheduler favours high ids, and an MMA issuer starved by eight busy epilogue warps stalls the tensor pipe
-// (measured: tile time 24.8 -> see profiles/).  The per-row polynomial coefficients U_p(yh_i) come from
-// k_poly_rows (one small launch per batch of screens).
+// (measured: tile time 24.8 -> see profiles/).  The epilogue is float32-only ON PURPOSE: on B200 the FP64 pipe does not
+// issue at all while tcgen05.mma instructions stream (tools/micro/fp64_vs_mma.cu: a DFMA loop takes exactly its own time
+// PLUS the MMA time), so any float64 in the epilogue serialises it with the MMAs of the next tile.  The low-ring
+// polynomial is therefore evaluated beforehand, in float64, at every 16th column (k_poly_rows -> k_poly_nodes, one
+// launch each per batch of screens) and stored as float32 triples (hi, lo, node value in turns).
 // Operands are pre-tiled in global memory by k_factors_tc in the canonical K-major / no-swizzle UMMA layout
 // (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
 #include <cuda_fp16.h>
+#include <cstdio>
 
 #include "common.cuh"
 #include "internal_screen.h"
@@ -198,6 +202,50 @@ __global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U, si
     U[(size_t)s * u_stride + (size_t)p * a.n + i] = fma(u1, yh, u0);
 }
 
+// ---- exact polynomial values at the interpolation nodes ----------------------------------------------------------
+// Node q (0 <= q < nq = n/16 + 5) sits at column 16 (q - 2) of the UNIFORM axis xu_j = x_first + j dxu (the reference's
+// float32 axis is that plus a rounding jitter of ~1e-7 m, which the epilogue puts back to first order through `jit`).
+// e(i, q) = sum_p U_p(yh_i) xh_q^p in float64 (Horner), stored for the float32 epilogue as
+//   nodes[screen][row block i/128][q]{hi, lo, turns}[i % 128]:  e = hi + lo,  turns = frac(e / 2 pi) reduced in float64.
+// One thread = one row x NODES_PT nodes.  grid: (n/128, ceil(nq / NODES_PT), nscreens), block 128.
+constexpr int NODES_PT = 19;
+constexpr int NODE_FLOATS = 3 * TM;          // floats per (row block, node)
+constexpr int TILE_NODES = TN / NODE_SP + 5; // nodes one output tile needs
+
+__global__ void __launch_bounds__(128) k_poly_nodes(ScreenLaunch a, const double* U, size_t u_stride, float* nodes, float* jit, int nq) {
+    const int n = a.n, D = a.degree;
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int q0 = blockIdx.y * NODES_PT;
+    const int s = blockIdx.z;
+    if (blockIdx.y == 0 && s == 0)          // column jitter of the float32 axis, in units of x0 (i is a column index here)
+        jit[i] = (float)(((double)__fadd_rn(a.x[i], a.shift_x) - (a.x_first + a.dxu * (double)i)) * a.inv_x0);
+    if (D < 0) return;
+    double xn[NODES_PT], e[NODES_PT];
+#pragma unroll
+    for (int t = 0; t < NODES_PT; ++t) {
+        xn[t] = (a.x_first + a.dxu * (double)((q0 + t - 2) * NODE_SP)) * a.inv_x0;
+        e[t] = 0.0;
+    }
+    const double* u = U + (size_t)s * u_stride + i;
+    for (int p = D; p >= 0; --p) {
+        const double up = __ldg(u + (size_t)p * n);
+#pragma unroll
+        for (int t = 0; t < NODES_PT; ++t) e[t] = fma(e[t], xn[t], up);
+    }
+    float* dst = nodes + (((size_t)s * (n / TM) + i / TM) * nq) * NODE_FLOATS + (i % TM);
+#pragma unroll
+    for (int t = 0; t < NODES_PT; ++t) {
+        const int q = q0 + t;
+        if (q >= nq) break;
+        const float hi = (float)e[t];
+        double tz = e[t] * 0.15915494309189533576888376;
+        tz -= rint(tz);
+        dst[(size_t)q * NODE_FLOATS] = hi;
+        dst[(size_t)q * NODE_FLOATS + TM] = (float)(e[t] - (double)hi);
+        dst[(size_t)q * NODE_FLOATS + 2 * TM] = (float)tz;
+    }
+}
+
 // 6-point Lagrange weights for nodes -2..3 at s = r/16 (sum to one; applied to differences from node 0)
 __device__ constexpr float kLag[16][6] = {
     {0.0000000000e+00f, 0.0000000000e+00f, 1.0000000000e+00f, 0.0000000000e+00f, 0.0000000000e+00f, 0.0000000000e+00f},
@@ -226,28 +274,32 @@ struct TcArgs {
     int total_tiles;    // nscreens * (n/128) * (n/256)
     int swap_lbo_sbo;   // debug bits: 1 = swap LBO/SBO, 2 = no bulk copies, 4 = no MMAs, 8 = no epilogue math (timing experiments)
     int* err;
-    const double* U;    // [nscreens][u_stride]: U_p(yh_i) = sum_q T_pq yh_i^q at [p * n + i]
-    size_t u_stride;
+    const float* nodes; // [nscreens][n/128][nq]{hi, lo, turns}[128]: polynomial at the interpolation nodes (k_poly_nodes)
+    const float* jit;   // [n] jitter of the float32 column axis around the uniform one, in units of x0
+    int nq;             // nodes per row = n/16 + 5
+    float inv_h;        // 1 / node spacing in normalised units
+    float out_scale;    // 1 / (p_scale * Q_SCALE): accumulator -> radians
+    long long* trace;   // debug bit 128: per-tile clock64 stamps of CTA 0, [tile][16]
 };
+#define PA_TRACE(slot) do { if (g.trace && blockIdx.x == 0 && it < 16) g.trace[it * 16 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
-    constexpr int SU_ROWS = kMaxPolyDegree + 1;
     extern __shared__ __align__(1024) unsigned char smem[];
     const ScreenLaunch& a = g.a;
     unsigned char* stage_base = smem;                                        // STAGES * STAGE_BYTES
-    double* sU = reinterpret_cast<double*>(smem + STAGES * STAGE_BYTES);     // [(D+1)][128] row coefficients of this tile
-    float* sX = reinterpret_cast<float*>(sU + (size_t)SU_ROWS * TM);          // [256] float32 jitter of the column axis (normalised)
+    float* sN = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [TILE_NODES]{hi, lo, turns}[128]: nodes of this tile
+    float* sX = sN + TILE_NODES * NODE_FLOATS;                               // [2][256] column jitter, per tile parity
     const int D = a.degree;
-    const double out_scale = 1.0 / (a.p_scale * (double)Q_SCALE);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + ((size_t)SU_ROWS * TM + TN / 2) * sizeof(double));
-    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * TN);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] nodes_full, [2S+5] nodes_free
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t ufull_bar = bar0 + 8u * (2 * STAGES + 4), ufree_bar = bar0 + 8u * (2 * STAGES + 5);
 
     constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;   // high warp ids: the scheduler favours them
     if (warp == W_MMA && lane == 0) {
@@ -259,6 +311,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             mbar_init(tfull_bar(b), 1);
             mbar_init(tempty_bar(b), EPI_WARPS);   // one arrival per epilogue warp
         }
+        mbar_init(ufull_bar, 1);
+        mbar_init(ufree_bar, EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == W_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
@@ -278,9 +332,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
                 const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
                 const int rb = rem / cblocks, cb = rem % cblocks;
+                PA_TRACE(0);
                 const char* psrc = (const char*)g.P + ((size_t)s * rblocks + rb) * g.kblocks * (size_t)P_STAGE;
                 const char* qsrc = (const char*)g.Q + ((size_t)s * cblocks + cb) * g.kblocks * (size_t)Q_STAGE;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
@@ -299,6 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
+                PA_TRACE(1);
             }
         }
     } else if (warp == W_MMA) {
@@ -311,8 +368,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             const uint32_t q_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(TN / 8) * 128u, q_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(TN / 8) * 128u : 128u;
             for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
                 const int buf = it & 1;
+                PA_TRACE(2);
                 mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);     // epilogue has drained this accumulator
                 tc_fence_after();
+                PA_TRACE(3);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
                     mbar_wait(full_bar(stage), phase, g.err);
@@ -333,90 +392,100 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 umma_commit(tfull_bar(buf));             // accumulator complete
+                PA_TRACE(4);
+            }
+        }
+    } else if (warp == W_ALLOC) {
+        // ===== node producer: the polynomial values of the next tile travel into sN as soon as the epilogue warps
+        // have read those of the current one =====
+        if (lane == 0 && D >= 0) {
+            int it = 0;
+            constexpr uint32_t BYTES = TILE_NODES * NODE_FLOATS * 4u, PIECE = BYTES / 3u;
+            static_assert(BYTES % 48 == 0, "three 16-byte aligned pieces");
+            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+                const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
+                const int rb = rem / cblocks, cb = rem % cblocks;
+                if (it > 0) mbar_wait(ufree_bar, (it - 1) & 1, g.err);
+                const char* src = reinterpret_cast<const char*>(g.nodes + (((size_t)s * rblocks + rb) * g.nq + (size_t)cb * (TN / NODE_SP)) * NODE_FLOATS);
+                mbar_expect_tx(ufull_bar, BYTES);
+#pragma unroll
+                for (uint32_t o = 0; o < BYTES; o += PIECE) bulk_g2s(smem_u32(sN) + o, src + o, PIECE, ufull_bar);
             }
         }
     } else if (warp < EPI_WARPS) {
-        // ===== epilogue: TMEM lane = output row; polynomial of the low rings + reduction to turns =====
-        // B200 issues only 32 DFMA/clk/SM, so float64 work bounds this epilogue.  The low-ring polynomial is smooth
-        // on the scale of tens of pixels (its highest harmonic has a wavelength of ~1000 pixels), so it is evaluated
-        // exactly (float64 Horner, degree D) only at every 16th column; in between, the DIFFERENCE from the nearest
-        // node (a few radians at most) is interpolated in float32 with 6-point Lagrange weights, and the node value
-        // itself is reduced mod 2 pi in float64.  Measured against the float64 path: < 2e-7 rad.
+        // ===== epilogue: TMEM lane = output row; low-ring polynomial + accumulator -> turns, float32 only =====
+        // The polynomial is smooth on the scale of tens of pixels (its highest harmonic has a wavelength of ~1000
+        // pixels): between two nodes the DIFFERENCE from the nearer-left node (a few radians at most) is interpolated
+        // with 6-point Lagrange weights, the node value itself arrives already reduced to turns, and the rounding jitter
+        // of the reference's float32 axis is put back to first order:  phi(x_j) = phi(xu_j) + (x_j - xu_j) dphi/dx.
+        // Measured against the float64 path: < 2e-7 rad.
         const int ew = warp & 3;                       // TMEM lane quarter this warp may read
         const int ch = warp >> 2;                      // which half of the 256 columns
         const int et = threadIdx.x;                    // index among the epilogue threads (warps 0..7)
         const int row_in_tile = ew * 32 + lane;
-        const float out_scale_f = (float)out_scale;
+        const float out_scale_f = g.out_scale;
         int it = 0;
         for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
             const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
             const int rb = rem / cblocks, cb = rem % cblocks;
             const int i = rb * TM + row_in_tile;
-            const double* U = g.U + (size_t)s * g.u_stride + i;        // U[p * n]: coalesced over the lanes of a warp
-            asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");     // previous tile's readers are done
-            for (int p = ch; p <= D; p += 2) sU[p * TM + row_in_tile] = __ldg(U + (size_t)p * n);
-            // Column coordinates.  The reference's axis is float32 (x_j = fl32(j * delta) + shift), i.e. a uniform
-            // axis plus a rounding jitter of ~1e-7 m.  Nodes sit on the UNIFORM axis xu_j = x_0 + j (x_{n-1}-x_0)/(n-1)
-            // + shift, and the jitter of every pixel is put back to first order:
-            // phi(x_j) = phi(xu_j) + (x_j - xu_j) dphi/dx   (second order ~1e-14).
-            const double x_first = (double)__ldg(a.x) + (double)a.shift_x;
-            const double dxu = ((double)__ldg(a.x + n - 1) - (double)__ldg(a.x)) / (double)(n - 1);
-            if (et < TN) {
-                const int jj = cb * TN + et;
-                sX[et] = (float)(((double)__fadd_rn(__ldg(a.x + jj), a.shift_x) - (x_first + dxu * (double)jj)) * a.inv_x0);
-            }
+            float* sXt = sX + (it & 1) * TN;           // the other parity may still be read by a slower warp
+            if (et < TN) sXt[et] = __ldg(g.jit + cb * TN + et);
             asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
-            const double* su = sU + row_in_tile;
             const int buf = it & 1;
+            if (threadIdx.x == 0) PA_TRACE(5);
             mbar_wait(tfull_bar(buf), (it >> 1) & 1, g.err);
             tc_fence_after();
+            if (D >= 0) mbar_wait(ufull_bar, it & 1, g.err);          // nodes of this tile have landed in sN
+            if (threadIdx.x == 0) PA_TRACE(6);
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
-                if (g.swap_lbo_sbo & 8) break;
+                if (g.swap_lbo_sbo & 8) {          // timing experiment without the epilogue math: only hand sN back
+                    __syncwarp();
+                    if (lane == 0 && D >= 0) mbar_arrive(ufree_bar);
+                    break;
+                }
                 const int cbase = ch * (TN / 2) + half * 64;            // first of the 64 columns of this round
                 const uint32_t t_row = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(buf * TN + cbase);
                 uint32_t acc0[32], acc1[32];
-                tmem_ld32_async(t_row, acc0);                            // in flight during the Horner evaluations below
-                // exact values at the 9 nodes cbase + 16 (kk - 2), kk = 0..8
-                double e[9];
-                {
-                    double xn[9];
+                tmem_ld32_async(t_row, acc0);
+                // the 9 nodes cbase + 16 (t - 2), t = 0..8, of this row
+                float nh[9], nl[9], nt[4];
+                if (D >= 0) {
+                    const float* sn = sN + (size_t)(cbase / NODE_SP) * NODE_FLOATS + row_in_tile;
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
-                        xn[t] = (x_first + dxu * (double)(cb * TN + cbase + NODE_SP * (t - 2))) * a.inv_x0;
-                        e[t] = 0.0;
+                        nh[t] = sn[t * NODE_FLOATS];
+                        nl[t] = sn[t * NODE_FLOATS + TM];
                     }
-                    if (!(g.swap_lbo_sbo & 32)) {
-                        int p = D;
-                        for (; p >= 1; p -= 2) {
-                            const double u0 = su[p * TM], u1 = su[(p - 1) * TM];
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u0);
+                    for (int k = 0; k < 4; ++k) nt[k] = sn[(k + 2) * NODE_FLOATS + 2 * TM];
+                } else {
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u1);
-                        }
-                        if (p == 0) {
-                            const double u0 = su[0];
+                    for (int t = 0; t < 9; ++t) nh[t] = nl[t] = 0.f;
 #pragma unroll
-                            for (int t = 0; t < 9; ++t) e[t] = fma(e[t], xn[t], u0);
-                        }
-                    }
+                    for (int k = 0; k < 4; ++k) nt[k] = 0.f;
+                }
+                if (threadIdx.x == 0) PA_TRACE(8 + 3 * half);
+                if (half == 1 && D >= 0) {        // sN is no longer needed by this warp: let the next tile's nodes come in
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(ufree_bar);
                 }
                 const int j0 = cb * TN + cbase;
                 float* turns = (a.turns && !(g.swap_lbo_sbo & 64)) ? (float*)a.turns + ((size_t)s * n + i) * n + j0 : nullptr;
-                const double inv_h = 1.0 / ((double)NODE_SP * dxu * a.inv_x0);   // 1 / node spacing in normalised units
                 tmem_wait_ld();                                          // first 32 accumulator columns have arrived
+                if (threadIdx.x == 0) PA_TRACE(9 + 3 * half);
                 tmem_ld32_async(t_row + 32u, acc1);                      // next 32 travel while these are finished
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {                            // interval between nodes k and k+1: 16 columns
+                for (int k = 0; k < 4; ++k) {                            // interval between nodes k+2 and k+3: 16 columns
                     if (k == 2) tmem_wait_ld();
-                    const double z0 = e[k + 2];
-                    double tz = z0 * 0.15915494309189533576888376;
-                    tz -= rint(tz);
-                    const float t1f = (float)tz;                         // node value in turns, reduced in float64
-                    const float d0 = (float)(e[k] - z0), d1 = (float)(e[k + 1] - z0), d3 = (float)(e[k + 3] - z0);
-                    const float d4 = (float)(e[k + 4] - z0), d5 = (float)(e[k + 5] - z0);
-                    const float slope = (float)((e[k + 3] - z0) * inv_h);
+                    const float zh = nh[k + 2], zl = nl[k + 2];
+                    const float t1f = nt[k];                             // node value in turns, reduced in float64 beforehand
+                    // hi parts are a few radians apart at magnitude <= 1e4: their difference is exact in float32
+                    const float d0 = (nh[k] - zh) + (nl[k] - zl), d1 = (nh[k + 1] - zh) + (nl[k + 1] - zl);
+                    const float d3 = (nh[k + 3] - zh) + (nl[k + 3] - zl), d4 = (nh[k + 4] - zh) + (nl[k + 4] - zl);
+                    const float d5 = (nh[k + 5] - zh) + (nl[k + 5] - zl);
+                    const float slope = d3 * g.inv_h;
                     float tv[16], dv[16];
 #pragma unroll
                     for (int r = 0; r < 16; ++r) {
@@ -427,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                         delta = fmaf(kLag[r][3], d3, delta);
                         delta = fmaf(kLag[r][4], d4, delta);
                         delta = fmaf(kLag[r][5], d5, delta);
-                        delta = fmaf(sX[cbase + c], slope, delta);
+                        delta = fmaf(sXt[cbase + c], slope, delta);
                         dv[r] = fmaf(accv, out_scale_f, delta);          // phase minus the node value (a few radians)
                         float tt = fmaf(dv[r], 0.15915494309189533577f, t1f);
                         tv[r] = tt - rintf(tt);
@@ -441,16 +510,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                         const size_t o = ((size_t)s * n + i) * n + j0 + 16 * k;
 #pragma unroll
                         for (int r = 0; r < 16; ++r) {
-                            const double ph = z0 + (double)dv[r];
+                            const double ph = (double)zh + (double)zl + (double)dv[r];
                             if (a.phi_f64) ((double*)a.phi)[o + r] = ph;
                             else ((float*)a.phi)[o + r] = (float)ph;
                         }
                     }
                 }
+                if (threadIdx.x == 0) PA_TRACE(10 + 3 * half);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (threadIdx.x == 0) PA_TRACE(7);
         }
     }
     tc_fence_before();
@@ -460,7 +531,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     }
 }
 
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ((kMaxPolyDegree + 1) * TM + TN / 2) * (int)sizeof(double) + (2 * STAGES + 4) * 8 + 16;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (TILE_NODES * NODE_FLOATS + 2 * TN) * (int)sizeof(float) + (2 * STAGES + 6) * 8 + 16;
 
 }  // namespace tc
 
@@ -468,8 +539,11 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + ((kMaxPolyDegree + 1) * TM + T
 size_t screen_tc_workspace(int n, int m, int m_split, int nscreens) {
     const int nhigh = m - m_split;
     const int kpad = ((2 * nhigh + tc::BK - 1) / tc::BK) * tc::BK;
+    const size_t nq = (size_t)n / tc::NODE_SP + 5;
     return (size_t)nscreens * 2 /*P,Q*/ * 2 /*hi,lo*/ * n * (size_t)(kpad > 0 ? kpad : tc::BK) * sizeof(__half) +
-           (size_t)nscreens * (kMaxPolyDegree + 1) * n * sizeof(double);      // + U table
+           (size_t)nscreens * (kMaxPolyDegree + 1) * n * sizeof(double) +                   // U table
+           (size_t)nscreens * (n / tc::TM) * nq * tc::NODE_FLOATS * sizeof(float) +         // node table
+           (size_t)n * sizeof(float);                                                        // column jitter
 }
 
 // phase: 0 = prepare only (operands + row coefficients for the a.nscreens screens of `a`, stored as screens
@@ -488,6 +562,11 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     __half* Pall = (__half*)workspace;
     __half* Qall = Pall + (size_t)total_screens * pq_stride;
     double* Uall = reinterpret_cast<double*>(Qall + (size_t)total_screens * pq_stride);
+    const int nq = a.n / NODE_SP + 5;
+    const size_t node_stride = (size_t)(a.n / TM) * nq * NODE_FLOATS;   // floats per screen
+    float* Nall = reinterpret_cast<float*>(Uall + (size_t)total_screens * u_stride);
+    float* jit = Nall + (size_t)total_screens * node_stride;
+    float* nodes = Nall + (size_t)first_screen * node_stride;
     __half* P = Pall + (size_t)first_screen * pq_stride;
     __half* Q = Qall + (size_t)first_screen * pq_stride;
     // row coefficients are packed with the actual degree: [(D+1)][n] per screen inside the reserved slab
@@ -499,6 +578,8 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
             dim3 gu(a.n / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride);
         }
+        dim3 gn(a.n / 128, (nq + NODES_PT - 1) / NODES_PT, a.nscreens);
+        k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
         if (phase == 0) return (int)cudaGetLastError();
     }
     static bool attr_done = false;
@@ -515,9 +596,31 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     g.total_tiles = a.nscreens * (a.n / TM) * (a.n / TN);
     g.swap_lbo_sbo = swap;
     g.err = err_flag;
-    g.U = U;
-    g.u_stride = u_stride;
+    g.nodes = nodes;
+    g.jit = jit;
+    g.nq = nq;
+    g.inv_h = (float)(1.0 / ((double)NODE_SP * a.dxu * a.inv_x0));
+    g.out_scale = (float)(1.0 / (a.p_scale * (double)Q_SCALE));
+    g.trace = nullptr;
     const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
+    if (swap & 128) {           // debug: clock64 stamps of CTA 0 printed to stderr (synchronises)
+        static long long* trace_dev = nullptr;
+        if (!trace_dev) cudaMalloc(&trace_dev, 16 * 16 * sizeof(long long));
+        cudaMemsetAsync(trace_dev, 0, 16 * 16 * sizeof(long long), st);
+        g.trace = trace_dev;
+        k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+        long long h[16 * 16];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
+        long long t0 = h[0];
+        fprintf(stderr, "k_screen_tc trace (CTA 0, cycles since first stamp): prod_start prod_end mma_wait mma_go mma_commit epi_wait epi_go epi_done | half0: horner tmem interp  half1: horner tmem interp\n");
+        for (int it = 0; it < 16 && h[it * 16] != 0; ++it) {
+            fprintf(stderr, "  tile %2d:", it);
+            for (int k = 0; k < 14; ++k) fprintf(stderr, " %9lld", h[it * 16 + k] ? h[it * 16 + k] - t0 : -1);
+            fprintf(stderr, "\n");
+        }
+        return (int)cudaGetLastError();
+    }
     k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
     return (int)cudaGetLastError();
 }
