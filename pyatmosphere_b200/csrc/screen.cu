@@ -59,39 +59,45 @@ __global__ void k_screen_factors64(ScreenLaunch a) {
 // grid: (nscreens, kPolySplit), block 256.  Rings are processed in chunks of 32: their power tables a^p, b^q
 // (p, q <= D) are built once per chunk in shared memory, then every thread accumulates its (p,q) pairs with one
 // DMUL + two DFMA per ring (the float64 pipe is the bound: 32 lanes/clk/SM on B200).  Entries with p+q > D are 0.
-constexpr int kPolySplit = 4;
+constexpr int kPolySplit = 8;
 constexpr int kPolyChunk = 32;
+// pairs of block y: rows p = y, y + kPolySplit, ... ; a thread's pairs have consecutive q within a warp, so the a^p
+// reads are broadcasts and the b^q reads are conflict-free.  320 blocks for 40 screens: one wave, 2-3 blocks per SM.
 __global__ void __launch_bounds__(256) k_screen_poly_coef(ScreenLaunch a) {
     const int D = a.degree, D1 = D + 1;
     const int s = blockIdx.x;
-    __shared__ double apow[kPolyChunk][kMaxPolyDegree + 1];
-    __shared__ double bpow[kPolyChunk][kMaxPolyDegree + 1];
+    constexpr int kPad = kMaxPolyDegree + 5;      // pitch of 68 doubles: the interleaved table build below is conflict-free
+    __shared__ double apow[kPolyChunk][kPad];
+    __shared__ double bpow[kPolyChunk][kPad];
     __shared__ double cre[kPolyChunk], cim[kPolyChunk];
-    // pairs handled by this block: index e = p * D1 + q with e % kPolySplit == blockIdx.y, up to 4 per thread
-    constexpr int kPer = ((kMaxPolyDegree + 1) * (kMaxPolyDegree + 1) + 256 * kPolySplit - 1) / (256 * kPolySplit);
+    constexpr int kRows = (kMaxPolyDegree + kPolySplit) / kPolySplit;                 // rows of p per block
+    constexpr int kPer = (kRows * (kMaxPolyDegree + 1) + 255) / 256;
     double sr[kPer], si[kPer];
-    int pe[kPer];
+    int pp[kPer], qq[kPer];
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
         sr[u] = 0.0;
         si[u] = 0.0;
-        const int e = (threadIdx.x + 256 * u) * kPolySplit + blockIdx.y;
-        pe[u] = (e < D1 * D1 && (e / D1 + e % D1) <= D) ? e : -1;
+        const int l = threadIdx.x + 256 * u;
+        const int p = blockIdx.y + kPolySplit * (l / D1), q = l % D1;
+        pp[u] = (p <= D && q <= D - p) ? p : -1;
+        qq[u] = q;
     }
     for (int m0 = 0; m0 < a.m_split; m0 += kPolyChunk) {
         __syncthreads();
-        if (threadIdx.x < 2 * kPolyChunk) {          // one thread per (ring, a-or-b) builds a power table
-            const int r = threadIdx.x >> 1, which = threadIdx.x & 1, m = m0 + r;
+        {   // four threads per (ring, a-or-b) build a power table: thread k fills the powers p = k (mod 4)
+            const int r = threadIdx.x >> 3, which = (threadIdx.x >> 2) & 1, part = threadIdx.x & 3, m = m0 + r;
             double base = 0.0;
             if (m < a.m_split)
                 base = 6.283185307179586476925287 * (which ? (double)a.fy[(size_t)s * a.m + m] * a.y0 : (double)a.fx[(size_t)s * a.m + m] * a.x0);
-            double w = 1.0;
+            const double b2 = base * base, b4 = b2 * b2;
+            double w = part == 0 ? 1.0 : (part == 1 ? base : (part == 2 ? b2 : b2 * base));
             double* row = which ? bpow[r] : apow[r];
-            for (int p = 0; p <= D; ++p) {
+            for (int p = part; p <= D; p += 4) {
                 row[p] = w;
-                w *= base;
+                w *= b4;
             }
-            if (!which) {
+            if (!which && part == 0) {
                 const float2 c = m < a.m_split ? a.coef[(size_t)s * a.m + m] : make_float2(0.f, 0.f);
                 cre[r] = (double)c.x;
                 cim[r] = (double)c.y;
@@ -100,27 +106,29 @@ __global__ void __launch_bounds__(256) k_screen_poly_coef(ScreenLaunch a) {
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < kPer; ++u) {
-            if (pe[u] < 0) continue;
-            const int p = pe[u] / D1, q = pe[u] % D1;
-            double tr = sr[u], ti = si[u];
+            if (pp[u] < 0) continue;
+            const int p = pp[u], q = qq[u];
+            double tr0 = sr[u], ti0 = si[u], tr1 = 0.0, ti1 = 0.0;       // two independent chains per pair
 #pragma unroll 4
-            for (int r = 0; r < kPolyChunk; ++r) {
-                const double w = apow[r][p] * bpow[r][q];
-                tr = fma(cre[r], w, tr);
-                ti = fma(cim[r], w, ti);
+            for (int r = 0; r < kPolyChunk; r += 2) {
+                const double w0 = apow[r][p] * bpow[r][q], w1 = apow[r + 1][p] * bpow[r + 1][q];
+                tr0 = fma(cre[r], w0, tr0);
+                ti0 = fma(cim[r], w0, ti0);
+                tr1 = fma(cre[r + 1], w1, tr1);
+                ti1 = fma(cim[r + 1], w1, ti1);
             }
-            sr[u] = tr;
-            si[u] = ti;
+            sr[u] = tr0 + tr1;
+            si[u] = ti0 + ti1;
         }
     }
     double* out = a.polyc + (size_t)s * D1 * D1;
 #pragma unroll
     for (int u = 0; u < kPer; ++u) {
-        const int e = (threadIdx.x + 256 * u) * kPolySplit + blockIdx.y;
-        if (e >= D1 * D1) continue;
+        const int l = threadIdx.x + 256 * u;
+        const int p = blockIdx.y + kPolySplit * (l / D1), q = l % D1;
+        if (p > D) continue;
         double v = 0.0;
-        if (pe[u] >= 0) {
-            const int p = e / D1, q = e % D1;
+        if (pp[u] >= 0) {
             switch ((p + q) & 3) {   // Re(i^k (sr + i si))
                 case 0: v = sr[u]; break;
                 case 1: v = -si[u]; break;
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(256) k_screen_poly_coef(ScreenLaunch a) {
             }
             v *= c_invfact[p] * c_invfact[q];
         }
-        out[e] = v;
+        out[p * D1 + q] = v;
     }
 }
 

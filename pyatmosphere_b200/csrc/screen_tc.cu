@@ -128,7 +128,7 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)
 // high ring are zero padding up to a multiple of 16 ranks (32 k).
 // One thread = one (row or column) x one k chunk of 8 = 4 rings.  grid: (n/128, kchunks, 2*nscreens), block 128.
 // The phase argument is reduced exactly in float64 (coord and frequency are float32, so their product is exact
-// in float64), then the trigonometry and the scaling run in float32: the operands only carry 22 bits (hi + lo).
+// in float64), then the trigonometry (MUFU) and the scaling run in float32: the operands only carry 22 bits (hi + lo).
 struct Split { __half hi, lo; };
 __device__ __forceinline__ Split split16(float v) {
     Split s;
@@ -156,8 +156,10 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
             const size_t o = (size_t)s * a.m + m;
             double turns = coord * (double)(is_q ? a.fx[o] : a.fy[o]);
             turns -= rint(turns);
-            float sn, cs;
-            sincospif(2.0f * (float)turns, &sn, &cs);
+            // |angle| <= pi after the exact reduction: the hardware approximations (abs. error ~4e-7 there) are as good
+            // as the 22-bit hi+lo operands, and four times cheaper than sincospif (this kernel is issue-bound)
+            const float ang = 6.283185307179586f * (float)turns;
+            const float sn = __sinf(ang), cs = __cosf(ang);
             if (is_q) {
                 v0 = cs * Q_SCALE;
                 v1 = sn * Q_SCALE;
@@ -227,8 +229,12 @@ __global__ void __launch_bounds__(128) k_poly_nodes(ScreenLaunch a, const double
         e[t] = 0.0;
     }
     const double* u = U + (size_t)s * u_stride + i;
-    for (int p = D; p >= 0; --p) {
-        const double up = __ldg(u + (size_t)p * n);
+    // the row coefficients of the block go through shared memory: all D+1 loads of a thread are in flight together
+    extern __shared__ double su_nodes[];                 // [(D+1)][128]
+#pragma unroll 8
+    for (int p = 0; p <= D; ++p) su_nodes[p * 128 + threadIdx.x] = __ldg(u + (size_t)p * n);
+    for (int p = D; p >= 0; --p) {                       // own column only: no barrier needed
+        const double up = su_nodes[p * 128 + threadIdx.x];
 #pragma unroll
         for (int t = 0; t < NODES_PT; ++t) e[t] = fma(e[t], xn[t], up);
     }
@@ -578,8 +584,14 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
             dim3 gu(a.n / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride);
         }
+        static bool nodes_attr_done = false;
+        if (!nodes_attr_done) {
+            cudaError_t e = cudaFuncSetAttribute(k_poly_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxPolyDegree + 1) * 128 * (int)sizeof(double));
+            if (e != cudaSuccess) return (int)e;
+            nodes_attr_done = true;
+        }
         dim3 gn(a.n / 128, (nq + NODES_PT - 1) / NODES_PT, a.nscreens);
-        k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
+        k_poly_nodes<<<gn, 128, (size_t)(a.degree >= 0 ? a.degree + 1 : 0) * 128 * sizeof(double), st>>>(a, U, u_stride, nodes, jit, nq);
         if (phase == 0) return (int)cudaGetLastError();
     }
     static bool attr_done = false;
