@@ -127,8 +127,8 @@ constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)
 // k = 2 r + {0,1} for ring rank r, where rank r is ring  m - 1 - r  (descending radius); ranks beyond the last
 // high ring are zero padding up to a multiple of 16 ranks (32 k).
 // One thread = one (row or column) x one k chunk of 8 = 4 rings.  grid: (n/128, kchunks, 2*nscreens), block 128.
-// The phase argument is reduced exactly in float64 (coord and frequency are float32, so their product is exact
-// in float64), then the trigonometry (MUFU) and the scaling run in float32: the operands only carry 22 bits (hi + lo).
+// The phase argument coord * f is reduced mod 1 with an error-free float32 product (hi + lo), then the trigonometry
+// (MUFU) and the scaling run in float32: the operands only carry 22 bits (hi + lo).
 struct Split { __half hi, lo; };
 __device__ __forceinline__ Split split16(float v) {
     Split s;
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
     const bool is_q = (blockIdx.z & 1) != 0;
     const int s = blockIdx.z >> 1;
     const int nhigh = a.m - a.m_split;
-    const double coord = is_q ? (double)__fadd_rn(a.x[idx], a.shift_x) : (double)__fadd_rn(a.y[idx], a.shift_y);
+    const float coord = is_q ? __fadd_rn(a.x[idx], a.shift_x) : __fadd_rn(a.y[idx], a.shift_y);
     const float pscale = (float)a.p_scale;
     __align__(16) __half hi[8];
     __align__(16) __half lo[8];
@@ -154,11 +154,15 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
         if (rank < nhigh) {
             const int m = a.m - 1 - rank;
             const size_t o = (size_t)s * a.m + m;
-            double turns = coord * (double)(is_q ? a.fx[o] : a.fy[o]);
-            turns -= rint(turns);
-            // |angle| <= pi after the exact reduction: the hardware approximations (abs. error ~4e-7 there) are as good
-            // as the 22-bit hi+lo operands, and four times cheaper than sincospif (this kernel is issue-bound)
-            const float ang = 6.283185307179586f * (float)turns;
+            // coord * f mod 1 without float64: the product is hi + lo exactly (lo from one FMA), hi - rint(hi) is exact,
+            // and |lo| <= ulp(hi)/2 ~ 1.5e-5 turns, so the sum is good to 3e-8 turns like a rounded float64 result
+            const float f = is_q ? a.fx[o] : a.fy[o];
+            const float hi_t = __fmul_rn(coord, f);
+            const float lo_t = __fmaf_rn(coord, f, -hi_t);
+            const float turns = (hi_t - rintf(hi_t)) + lo_t;
+            // |angle| <= pi (+ 1e-4): the hardware approximations (abs. error ~4e-7 there) are as good as the 22-bit
+            // hi+lo operands, and four times cheaper than sincospif (this kernel is issue-bound)
+            const float ang = 6.283185307179586f * turns;
             const float sn = __sinf(ang), cs = __cosf(ang);
             if (is_q) {
                 v0 = cs * Q_SCALE;
