@@ -461,6 +461,8 @@ static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coe
     a.inv_y0 = 1 / y0;
     a.x_first = (double)c->hx[0] + (double)a.shift_x;
     a.dxu = ((double)c->hx[n - 1] - (double)c->hx[0]) / (double)(n - 1);
+    a.y_first = (double)c->hy[0] + (double)a.shift_y;
+    a.dyu = ((double)c->hy[n - 1] - (double)c->hy[0]) / (double)(n - 1);
     a.fx = fx;
     a.fy = fy;
     a.coef = (const float2*)coef;

@@ -27,8 +27,8 @@ struct ScreenLaunch {
     void* phi;          // out, optional full phase [nscreens][n][n] float or double
     int phi_f64;
     double p_scale;     // tensor-core path: power-of-two scale of the P operand (fp16 range)
-    // uniform column axis underlying the float32 one (tensor-core path): xu_j = x_first + j * dxu, shift included
-    double x_first, dxu;
+    // uniform axes underlying the float32 ones (tensor-core path): xu_j = x_first + j * dxu, shift included
+    double x_first, dxu, y_first, dyu;
 };
 
 int screen_init_constants();

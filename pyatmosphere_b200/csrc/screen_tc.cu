@@ -189,15 +189,29 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
     *reinterpret_cast<uint4*>(dst + half_bytes) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// ---- per-row polynomial coefficients: U[s][p][i] = sum_{q <= D-p} T_pq yh_i^q ---------------------------------
-// grid: (n/128, D+1, nscreens), block 128: one (row, p) per thread.
-__global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U, size_t u_stride) {
+// ---- low-ring polynomial at the interpolation nodes --------------------------------------------------------------
+// Nodes sit every NODE_SP pixels of the UNIFORM axes xu_j = x_first + j dxu (the reference's float32 axes are those plus a
+// rounding jitter of ~1e-7 m): node q (0 <= q < nq = n/16 + 5) is pixel 16 (q - 2), in x and in y alike.
+//   k_poly_rows   : Uc[s][p][qy] = sum_q' T_pq' yh(qy)^q'          grid (ceil(nq/128), D+1, nscreens)
+//   k_poly_coarse : E[s][qy][qx] = sum_p Uc[s][p][qy] xh(qx)^p      grid (ceil(nq^2/128), 1, nscreens)  (float64 Horner)
+//   k_poly_nodes  : e(i, qx) = sum_t w_t(s_i) E[s][b_i + t][qx]     6-point Lagrange in y at the ACTUAL position of row i,
+//                   stored for the float32 epilogue as nodes[screen][row block i/128][qx]{hi, lo, turns}[i % 128]:
+//                   e = hi + lo, turns = frac(e / 2 pi) reduced in float64; also writes the column jitter table.
+// Interpolating the exact values of every 16th row instead of evaluating every row exactly costs < 1.5e-7 rad (the
+// polynomial is as smooth in y as in x) and 5x fewer float64 operations, which B200 is short of (32 DFMA/clk/SM).
+// Per-screen scratch inside the workspace slab of u_stride doubles: Uc at 0, E at (kMaxPolyDegree + 1) * nq.
+constexpr int NODES_PT = 19;
+constexpr int NODE_FLOATS = 3 * TM;          // floats per (row block, node)
+constexpr int TILE_NODES = TN / NODE_SP + 5; // nodes one output tile needs
+
+__global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* W, size_t u_stride, int nq) {
     const int D = a.degree;
-    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int i = blockIdx.x * 128 + threadIdx.x;      // row node
     const int p = blockIdx.y;
     const int s = blockIdx.z;
+    if (i >= nq) return;
     const double* tcf = a.polyc + (size_t)s * (D + 1) * (D + 1) + (size_t)p * (D + 1);
-    const double yh = (double)__fadd_rn(a.y[i], a.shift_y) * a.inv_y0;
+    const double yh = (a.y_first + a.dyu * (double)((i - 2) * NODE_SP)) * a.inv_y0;
     double u0 = 0.0, u1 = 0.0;                 // even / odd powers separately: two independent Horner chains in yh^2
     const double y2 = yh * yh;
     const int top = D - p;
@@ -205,20 +219,29 @@ __global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* U, si
         if ((q & 1) == 0) u0 = fma(u0, y2, __ldg(tcf + q));
         else u1 = fma(u1, y2, __ldg(tcf + q));
     }
-    U[(size_t)s * u_stride + (size_t)p * a.n + i] = fma(u1, yh, u0);
+    W[(size_t)s * u_stride + (size_t)p * nq + i] = fma(u1, yh, u0);
 }
 
-// ---- exact polynomial values at the interpolation nodes ----------------------------------------------------------
-// Node q (0 <= q < nq = n/16 + 5) sits at column 16 (q - 2) of the UNIFORM axis xu_j = x_first + j dxu (the reference's
-// float32 axis is that plus a rounding jitter of ~1e-7 m, which the epilogue puts back to first order through `jit`).
-// e(i, q) = sum_p U_p(yh_i) xh_q^p in float64 (Horner), stored for the float32 epilogue as
-//   nodes[screen][row block i/128][q]{hi, lo, turns}[i % 128]:  e = hi + lo,  turns = frac(e / 2 pi) reduced in float64.
-// One thread = one row x NODES_PT nodes.  grid: (n/128, ceil(nq / NODES_PT), nscreens), block 128.
-constexpr int NODES_PT = 19;
-constexpr int NODE_FLOATS = 3 * TM;          // floats per (row block, node)
-constexpr int TILE_NODES = TN / NODE_SP + 5; // nodes one output tile needs
+__global__ void __launch_bounds__(128) k_poly_coarse(ScreenLaunch a, double* W, size_t u_stride, int nq) {
+    const int D = a.degree;
+    const int l = blockIdx.x * 128 + threadIdx.x, s = blockIdx.z;
+    if (l >= nq * nq) return;
+    const int qy = l / nq, qx = l % nq;
+    const double xh = (a.x_first + a.dxu * (double)((qx - 2) * NODE_SP)) * a.inv_x0;
+    const double* u = W + (size_t)s * u_stride + qy;
+    double e[4] = {0.0, 0.0, 0.0, 0.0};        // four Horner chains in xh^4 (the chain latency bounds this small kernel)
+    const double x2 = xh * xh, x4 = x2 * x2;
+    for (int p4 = D / 4; p4 >= 0; --p4) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int p = 4 * p4 + c;
+            e[c] = fma(e[c], x4, p <= D ? __ldg(u + (size_t)p * nq) : 0.0);
+        }
+    }
+    W[(size_t)s * u_stride + (size_t)(kMaxPolyDegree + 1) * nq + (size_t)qy * nq + qx] = fma(fma(e[3], xh, e[2]), x2, fma(e[1], xh, e[0]));
+}
 
-__global__ void __launch_bounds__(128) k_poly_nodes(ScreenLaunch a, const double* U, size_t u_stride, float* nodes, float* jit, int nq) {
+__global__ void __launch_bounds__(128) k_poly_nodes(ScreenLaunch a, const double* W, size_t u_stride, float* nodes, float* jit, int nq) {
     const int n = a.n, D = a.degree;
     const int i = blockIdx.x * 128 + threadIdx.x;
     const int q0 = blockIdx.y * NODES_PT;
@@ -226,32 +249,32 @@ __global__ void __launch_bounds__(128) k_poly_nodes(ScreenLaunch a, const double
     if (blockIdx.y == 0 && s == 0)          // column jitter of the float32 axis, in units of x0 (i is a column index here)
         jit[i] = (float)(((double)__fadd_rn(a.x[i], a.shift_x) - (a.x_first + a.dxu * (double)i)) * a.inv_x0);
     if (D < 0) return;
-    double xn[NODES_PT], e[NODES_PT];
-#pragma unroll
-    for (int t = 0; t < NODES_PT; ++t) {
-        xn[t] = (a.x_first + a.dxu * (double)((q0 + t - 2) * NODE_SP)) * a.inv_x0;
-        e[t] = 0.0;
-    }
-    const double* u = U + (size_t)s * u_stride + i;
-    // the row coefficients of the block go through shared memory: all D+1 loads of a thread are in flight together
-    extern __shared__ double su_nodes[];                 // [(D+1)][128]
-#pragma unroll 8
-    for (int p = 0; p <= D; ++p) su_nodes[p * 128 + threadIdx.x] = __ldg(u + (size_t)p * n);
-    for (int p = D; p >= 0; --p) {                       // own column only: no barrier needed
-        const double up = su_nodes[p * 128 + threadIdx.x];
-#pragma unroll
-        for (int t = 0; t < NODES_PT; ++t) e[t] = fma(e[t], xn[t], up);
-    }
+    // Lagrange weights of row nodes b-2 .. b+3 (b = the node at or below row i) at the actual float32 row coordinate
+    const int r = i % NODE_SP;
+    const double sy = ((double)__fadd_rn(a.y[i], a.shift_y) - (a.y_first + a.dyu * (double)(i - r))) / ((double)NODE_SP * a.dyu);
+    const double m2 = sy + 2.0, m1 = sy + 1.0, p1 = sy - 1.0, p2 = sy - 2.0, p3 = sy - 3.0;
+    double w[6];
+    w[0] = m1 * sy * p1 * p2 * p3 * (-1.0 / 120.0);
+    w[1] = m2 * sy * p1 * p2 * p3 * (1.0 / 24.0);
+    w[2] = m2 * m1 * p1 * p2 * p3 * (-1.0 / 12.0);
+    w[3] = m2 * m1 * sy * p2 * p3 * (1.0 / 12.0);
+    w[4] = m2 * m1 * sy * p1 * p3 * (-1.0 / 24.0);
+    w[5] = m2 * m1 * sy * p1 * p2 * (1.0 / 120.0);
+    // row nodes b-2 .. b+3 are rows (i / 16) .. (i / 16) + 5 of E
+    const double* E = W + (size_t)s * u_stride + (size_t)(kMaxPolyDegree + 1) * nq + (size_t)(i / NODE_SP) * nq;
     float* dst = nodes + (((size_t)s * (n / TM) + i / TM) * nq) * NODE_FLOATS + (i % TM);
 #pragma unroll
     for (int t = 0; t < NODES_PT; ++t) {
         const int q = q0 + t;
         if (q >= nq) break;
-        const float hi = (float)e[t];
-        double tz = e[t] * 0.15915494309189533576888376;
+        double e = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) e = fma(w[k], __ldg(E + (size_t)k * nq + q), e);
+        const float hi = (float)e;
+        double tz = e * 0.15915494309189533576888376;
         tz -= rint(tz);
         dst[(size_t)q * NODE_FLOATS] = hi;
-        dst[(size_t)q * NODE_FLOATS + TM] = (float)(e[t] - (double)hi);
+        dst[(size_t)q * NODE_FLOATS + TM] = (float)(e - (double)hi);
         dst[(size_t)q * NODE_FLOATS + 2 * TM] = (float)tz;
     }
 }
@@ -585,17 +608,13 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
         k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
         if (a.degree >= 0) {
-            dim3 gu(a.n / 128, a.degree + 1, a.nscreens);
-            k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride);
-        }
-        static bool nodes_attr_done = false;
-        if (!nodes_attr_done) {
-            cudaError_t e = cudaFuncSetAttribute(k_poly_nodes, cudaFuncAttributeMaxDynamicSharedMemorySize, (kMaxPolyDegree + 1) * 128 * (int)sizeof(double));
-            if (e != cudaSuccess) return (int)e;
-            nodes_attr_done = true;
+            dim3 gu((nq + 127) / 128, a.degree + 1, a.nscreens);
+            k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride, nq);
+            dim3 gc((nq * nq + 127) / 128, 1, a.nscreens);
+            k_poly_coarse<<<gc, 128, 0, st>>>(a, U, u_stride, nq);
         }
         dim3 gn(a.n / 128, (nq + NODES_PT - 1) / NODES_PT, a.nscreens);
-        k_poly_nodes<<<gn, 128, (size_t)(a.degree >= 0 ? a.degree + 1 : 0) * 128 * sizeof(double), st>>>(a, U, u_stride, nodes, jit, nq);
+        k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
         if (phase == 0) return (int)cudaGetLastError();
     }
     static bool attr_done = false;
