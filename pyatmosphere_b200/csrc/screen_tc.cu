@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
 // Nodes sit every NODE_SP pixels of the UNIFORM axes xu_j = x_first + j dxu (the reference's float32 axes are those plus a
 // rounding jitter of ~1e-7 m): node q (0 <= q < nq = n/16 + 5) is pixel 16 (q - 2), in x and in y alike.
 //   k_poly_rows   : Uc[s][p][qy] = sum_q' T_pq' yh(qy)^q'          grid (ceil(nq/128), D+1, nscreens)
-//   k_poly_coarse : E[s][qy][qx] = sum_p Uc[s][p][qy] xh(qx)^p      grid (ceil(nq^2/128), 1, nscreens)  (float64 Horner)
+//   k_poly_coarse : E[s][qy][qx] = sum_p Uc[s][p][qy] xh(qx)^p      grid (ceil(nq/160), nq, nscreens)   (float64 Horner)
 //   k_poly_nodes  : e(i, qx) = sum_t w_t(s_i) E[s][b_i + t][qx]     6-point Lagrange in y at the ACTUAL position of row i,
 //                   stored for the float32 epilogue as nodes[screen][row block i/128][qx]{hi, lo, turns}[i % 128]:
 //                   e = hi + lo, turns = frac(e / 2 pi) reduced in float64; also writes the column jitter table.
@@ -222,21 +222,20 @@ __global__ void __launch_bounds__(128) k_poly_rows(ScreenLaunch a, double* W, si
     W[(size_t)s * u_stride + (size_t)p * nq + i] = fma(u1, yh, u0);
 }
 
-__global__ void __launch_bounds__(128) k_poly_coarse(ScreenLaunch a, double* W, size_t u_stride, int nq) {
+__global__ void __launch_bounds__(160) k_poly_coarse(ScreenLaunch a, double* W, size_t u_stride, int nq) {
     const int D = a.degree;
-    const int l = blockIdx.x * 128 + threadIdx.x, s = blockIdx.z;
-    if (l >= nq * nq) return;
-    const int qy = l / nq, qx = l % nq;
+    const int qx = blockIdx.x * 160 + threadIdx.x, qy = blockIdx.y, s = blockIdx.z;
+    __shared__ double su[kMaxPolyDegree + 4];            // coefficients of this row node: one load latency, then broadcasts
+    if (threadIdx.x < kMaxPolyDegree + 4)
+        su[threadIdx.x] = threadIdx.x <= D ? __ldg(W + (size_t)s * u_stride + (size_t)threadIdx.x * nq + qy) : 0.0;
+    __syncthreads();
+    if (qx >= nq) return;
     const double xh = (a.x_first + a.dxu * (double)((qx - 2) * NODE_SP)) * a.inv_x0;
-    const double* u = W + (size_t)s * u_stride + qy;
-    double e[4] = {0.0, 0.0, 0.0, 0.0};        // four Horner chains in xh^4 (the chain latency bounds this small kernel)
+    double e[4] = {0.0, 0.0, 0.0, 0.0};        // four Horner chains in xh^4
     const double x2 = xh * xh, x4 = x2 * x2;
     for (int p4 = D / 4; p4 >= 0; --p4) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int p = 4 * p4 + c;
-            e[c] = fma(e[c], x4, p <= D ? __ldg(u + (size_t)p * nq) : 0.0);
-        }
+        for (int c = 0; c < 4; ++c) e[c] = fma(e[c], x4, su[4 * p4 + c]);
     }
     W[(size_t)s * u_stride + (size_t)(kMaxPolyDegree + 1) * nq + (size_t)qy * nq + qx] = fma(fma(e[3], xh, e[2]), x2, fma(e[1], xh, e[0]));
 }
@@ -610,8 +609,8 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         if (a.degree >= 0) {
             dim3 gu((nq + 127) / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride, nq);
-            dim3 gc((nq * nq + 127) / 128, 1, a.nscreens);
-            k_poly_coarse<<<gc, 128, 0, st>>>(a, U, u_stride, nq);
+            dim3 gc((nq + 159) / 160, nq, a.nscreens);
+            k_poly_coarse<<<gc, 160, 0, st>>>(a, U, u_stride, nq);
         }
         dim3 gn(a.n / 128, (nq + NODES_PT - 1) / NODES_PT, a.nscreens);
         k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
