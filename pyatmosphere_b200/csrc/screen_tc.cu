@@ -116,6 +116,11 @@ __device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t (&r)[32
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // instruction descriptor: fp32 accumulate, fp16 A and B, both K-major, M = 128, N = 256
@@ -533,10 +538,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                         float tt = fmaf(dv[r], 0.15915494309189533577f, t1f);
                         tv[r] = tt - rintf(tt);
                     }
-                    if (turns) {
+                    if (turns) {        // 256-bit stores: every lane writes whole 32-byte sectors of its own row
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(turns + 16 * k + 4 * q) = make_float4(tv[4 * q], tv[4 * q + 1], tv[4 * q + 2], tv[4 * q + 3]);
+                        for (int q = 0; q < 2; ++q)
+                            st_global_v8(turns + 16 * k + 8 * q, tv + 8 * q);
                     }
                     if (a.phi) {                                         // full phase requested (generator / inspection path)
                         const size_t o = ((size_t)s * n + i) * n + j0 + 16 * k;
