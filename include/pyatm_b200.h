@@ -81,6 +81,16 @@ PA_API int pa_screen_ss(pa_ctx* ctx, const float* fx_dev, const float* fy_dev, c
                  int degree, double shift_x, double shift_y, int nscreens, void* turns_dev, void* phi_dev,
                  int phi_f64, int method, double coef_bound, void* stream);
 
+/* phase_screens.py:37-67 FFTPhaseScreen.generate_phase_screen:  ifft2(cn, 1) [utils.py:47-50] + subharmonic terms
+ * [:55-65] - mean [:67].
+ * spectrum_dev: [nscreens][N][N] complex (context precision), the coefficients cn of :43-47 in the reference's
+ * centred frequency order (index N/2 = zero frequency, row <-> first index of cn).
+ * terms_host: [nscreens][nterms][4] doubles {fx, fy, Re c, Im c}: the screen gains  c * exp(2 pi i (fx x_j + fy y_i));
+ * nterms may be 0.  Outputs (either may be NULL): the complex screen and/or its real part, [nscreens][N][N], context
+ * precision.  Not in place: spectrum_dev is only read. */
+PA_API int pa_screen_fft(pa_ctx* ctx, const void* spectrum_dev, int nscreens, const double* terms_host, int nterms,
+                  void* out_complex_dev, void* out_real_dev, void* stream);
+
 /* pathes.py:72-73  u <- scale * exp(-i phi) * u  with phi given in turns (see pa_phase_to_turns) */
 PA_API int pa_apply_screen(pa_ctx* ctx, void* field_dev, int batch, const void* turns_dev, double scale, void* stream);
 PA_API int pa_phase_to_turns(pa_ctx* ctx, const void* phi_dev, int phi_f64, void* turns_dev, size_t count, void* stream);

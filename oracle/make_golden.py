@@ -168,6 +168,65 @@ def case_time_series(pa, p, seed, count, times):
                         versions=_versions(), **params_arrays(p))
 
 
+def _run_and_record(ch, seed):
+    """Channel.generator drained (per-leg fields and screens), then Channel.run re-seeded, as export_realization."""
+    np.random.seed(seed)
+    legs, screens = [], []
+    for u, phi in ch.generator(pupil=False, store_output=True):
+        legs.append(np.asarray(u)); screens.append(np.asarray(phi))
+    np.random.seed(seed)
+    out_run = np.asarray(ch.run(pupil=False))
+    return np.stack(screens), np.stack(legs), out_run
+
+
+def case_su(pa, p, seed):
+    """SUPhaseScreen channel (phase_screens.py:154-179): exported draws, per-leg screens and fields, output field."""
+    ch = pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]),
+        source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.SUPhaseScreen(
+                model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
+                f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])),
+            length=p["length"], count=p["count"]),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
+    screens, legs, out = _run_and_record(ch, seed)
+    np.savez_compressed(os.path.join(OUT, "su128.npz"), seed=seed, screens=screens, legs=legs, field=out,
+                        measures=measures_of(pa, ch, out), versions=_versions(), **params_arrays(p))
+
+
+def case_fft(pa, p, seed):
+    """FFTPhaseScreen channel (phase_screens.py:37-67) with subharmonic levels.  The coefficient arrays handed to
+    ifft2 are captured by wrapping the name the reference module calls (the reference code itself is untouched)."""
+    ch = pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]),
+        source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.FFTPhaseScreen(p["subharmonics"], model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])),
+            length=p["length"], count=p["count"]),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
+    mod = pa.phase_screens
+    captured, plain = [], mod.ifft2
+
+    def spy(x, delta):
+        captured.append(np.array(x))
+        return plain(x, delta)
+
+    mod.ifft2 = spy
+    try:
+        screens, legs, out = _run_and_record(ch, seed)
+    finally:
+        mod.ifft2 = plain
+    cn0 = captured[0]
+    # one complex screen straight from the generator's first draw (real and imaginary parts both checked)
+    ch.path.init_phase_screens()
+    np.random.seed(seed)
+    full0 = np.asarray(ch.path.phase_screens[0].generate(complex=True))
+    np.savez_compressed(os.path.join(OUT, "fft128.npz"), seed=seed, screens=screens, legs=legs, field=out,
+                        cn0_checksum=np.array([cn0.sum(), np.abs(cn0).sum()]), cn0_corner=cn0[:8, :8], cn0_dtype=str(cn0.dtype),
+                        screen0_complex=full0, measures=measures_of(pa, ch, out), versions=_versions(), **params_arrays(p))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     pa = _import_reference()
@@ -185,9 +244,21 @@ def main():
     case_turbulent(pa, "quick256", quick, seed=5, with_legs=False)
     case_simulation(pa, small, seed=2024, count=6)
     case_time_series(pa, small, seed=77, count=3, times=(0.0, 0.012, 0.05))
+    case_su(pa, dict(small, count=2), seed=31)
+    case_fft(pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
+                      pupil=0.1, subharmonics=2), seed=13)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-n4":      # add the SU / FFT fixtures without touching the others
+        os.makedirs(OUT, exist_ok=True)
+        _pa = _import_reference()
+        _small = dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, m=96,
+                      f_min=1 / 1e2 / 15, f_max=1 / 8e-3, length=6e3, count=2, pupil=0.1)
+        case_su(_pa, _small, seed=31)
+        case_fft(_pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
+                           pupil=0.1, subharmonics=2), seed=13)
+    else:
+        main()

@@ -31,6 +31,8 @@ __all__ = [
     "draw_spectrum", "spectrum_to_fxy", "ss_screen", "gaussian_source", "gaussian_width", "vacuum_leg",
     "screen_positions", "leg_lengths", "propagate", "circle_mask", "intensity", "moments", "rytov2",
     "analytic_gaussian_field", "pdt_histogram", "beam_statistics",
+    "psd_phi_f", "andrews_psd_n", "su_delta_k", "draw_su_spectrum", "fft_screen_coefficients", "draw_fft_screen",
+    "fft_screen",
 ]
 
 
@@ -128,13 +130,18 @@ def spectrum_to_fxy(rho: np.ndarray, theta: np.ndarray):
 # --------------------------------------------------------------------------------------------------
 # sparse-spectrum screen
 # --------------------------------------------------------------------------------------------------
-def ss_screen(x, y, fx, fy, value, shift=(0.0, 0.0), mode: str = "ref", complex_out: bool = False):
+def ss_screen(x, y, fx, fy, value, shift=(0.0, 0.0), mode: str = "ref", complex_out: bool = False,
+              diag_product: bool = False):
     """phi[i,j] = Re sum_m value_m exp(2 pi i (y_i+sy) fy_m) exp(2 pi i fx_m (x_j+sx)).
 
     phase_screens.py:108-126 (contraction at :125-126), `.real` at :25-28.
     x (1,N), y (N,1) float32; fx (1,M), fy (M,1) float32; value (M,) complex64.
-    mode="ref": float32/complex64 arithmetic like the reference; mode="f64": inputs promoted exactly."""
-    if mode == "ref":
+    mode="ref": float32/complex64 arithmetic like the reference; mode="f64": inputs promoted exactly.
+    diag_product=True evaluates the "ref" mode as  E_y @ diag(value) @ E_x, the operation order of SUPhaseScreen
+    (phase_screens.py:179); the value is the same sum, only the complex64 rounding differs."""
+    if mode == "ref" and diag_product:
+        full = np.exp(1j * 2 * np.pi * (y + shift[1]) @ fy.T) @ np.diag(value) @ np.exp(1j * 2 * np.pi * fx.T @ (x + shift[0]))
+    elif mode == "ref":
         xs = x + shift[0]
         ys = y + shift[1]
         left = value * np.exp(1j * 2 * np.pi * ys @ fy.T)          # (N,M) complex64
@@ -152,6 +159,89 @@ def ss_screen(x, y, fx, fy, value, shift=(0.0, 0.0), mode: str = "ref", complex_
     else:
         raise ValueError(mode)
     return full if complex_out else full.real
+
+
+# --------------------------------------------------------------------------------------------------
+# the other screen generators
+# --------------------------------------------------------------------------------------------------
+def andrews_psd_n(kappa, Cn2: float, l0: float, L0: float):
+    """Andrews' spectrum with the inner-scale bump (theory/models.py:94-101)."""
+    kl = 3.3 / l0
+    k0 = (2 * np.pi) / L0
+    q = kappa / kl
+    return 0.033 * Cn2 * (1 + 1.802 * q - 0.254 * q ** (7 / 6)) * np.exp(-(q) ** 2) / (kappa**2 + k0**2) ** (11 / 6)
+
+
+def psd_phi_f(f, Cn2: float, l0: float, L0: float, k: float, thickness: float, psd_n=mvk_psd_n):
+    """Phase spectrum of a slab over spatial frequency f: 2 pi k^2 dz Phi_n(2 pi f) (theory/models.py:16-23)."""
+    return 2 * np.pi * k**2 * thickness * psd_n(2 * np.pi * f, Cn2, l0, L0)
+
+
+def su_delta_k(base: np.ndarray) -> np.ndarray:
+    """(2 pi)^2 (f_m^2 - f_{m-1}^2), float32: area of annulus m in kappa-space over pi (phase_screens.py:160-165)."""
+    return (2 * np.pi) ** 2 * np.array(base**2 - np.insert(base, 0, 0)[:-1] ** 2, dtype=np.float32)
+
+
+def draw_su_spectrum(base: np.ndarray, Cn2: float, l0: float, L0: float, wvl: float, thickness: float, psd_n=mvk_psd_n):
+    """Sparse-uniform coefficients (phase_screens.py:166-176), drawn from numpy's GLOBAL RNG in the reference's order
+    (random(1), random(M), normal(2,M)):  c_m = (n0 + i n1) sqrt(psd_phi_f(rho_m) pi dk_m), complex64."""
+    m = len(base)
+    rand = np.random.random(size=(1,)).astype(np.float32)
+    rho = ring_rho(base, rand)
+    theta = 2 * np.pi * np.random.random(size=(m,)).astype(np.float32)
+    noise = (np.array([1, 1j]) @ np.random.normal(size=(2, m))).astype(np.complex64)
+    value = noise * np.sqrt(psd_phi_f(rho, Cn2, l0, L0, 2 * np.pi / wvl, thickness, psd_n) * np.pi * su_delta_k(base))
+    return rho, theta, value
+
+
+def fft_screen_coefficients(points: int, delta_f, Cn2: float, l0: float, L0: float, wvl: float, thickness: float,
+                            psd_n=mvk_psd_n):
+    """One draw of phase_screens.py:43-48 on the centred frequency grid RectGrid(points, delta_f): real normals
+    first, then the imaginary ones; cn = noise(c64) * sqrt(psd_phi_f(|f|)) * 2 pi delta_f, centre element zeroed.
+    `delta_f` is a numpy float64 in the reference (grids.py:82-85), which promotes the frequency axis -- and with
+    it cn -- to double precision under numpy >= 2."""
+    noise = (np.random.normal(size=(points, points)) + 1j * np.random.normal(size=(points, points))).astype(np.complex64)
+    ax = rect_axis(points, 1.0).astype(np.float32) * delta_f
+    rho = np.sqrt(ax.reshape(1, -1) ** 2 + ax.reshape(-1, 1) ** 2)
+    cn = noise * np.sqrt(psd_phi_f(rho, Cn2, l0, L0, 2 * np.pi / wvl, thickness, psd_n)) * 2 * np.pi * delta_f
+    cn[points // 2, points // 2] = 0
+    return cn
+
+
+def draw_fft_screen(n: int, delta: float, subharmonics: int, Cn2: float, l0: float, L0: float, wvl: float,
+                    thickness: float, psd_n=mvk_psd_n):
+    """All random inputs of one FFT screen in the reference's draw order (phase_screens.py:50-58): the n x n
+    coefficients, then for every subharmonic level a 3 x 3 patch with spacing delta_f / 3^(level+1).
+    Returns (cn, terms) with terms[t] = (fx, fy, c): the screen gains c exp(2 pi i (fx x + fy y))."""
+    df = f_grid_delta(n, delta)
+    cn = fft_screen_coefficients(n, df, Cn2, l0, L0, wvl, thickness, psd_n)
+    terms = []
+    for level in range(subharmonics):
+        dsub = df / 3 ** (level + 1)
+        c = fft_screen_coefficients(3, dsub, Cn2, l0, L0, wvl, thickness, psd_n)
+        f = rect_axis(3, 1.0).astype(np.float32) * dsub
+        for i in range(3):
+            for j in range(3):
+                terms.append((f[i], f[j], c[i, j]))          # f[i] pairs with x, f[j] with y (phase_screens.py:63-65)
+    return cn, terms
+
+
+def fft_screen(cn, terms, x, y, mode: str = "ref"):
+    """Complex FFT screen (phase_screens.py:50-67): ifft2(cn, 1) [utils.py:47-50] + sum of the subharmonic terms, minus
+    the mean.  mode="ref" lets numpy pick the dtypes as in the reference (double precision under numpy >= 2 because cn
+    and the subharmonic frequencies are float64-based); mode="f64" promotes every input explicitly."""
+    if mode == "f64":
+        cn = np.asarray(cn, dtype=np.complex128)
+        x = x.astype(np.float64)
+        y = y.astype(np.float64)
+    elif mode != "ref":
+        raise ValueError(mode)
+    screen = _centred_ifft2(cn, 1)
+    for fx, fy, c in terms:
+        if mode == "f64":
+            fx, fy, c = np.float64(fx), np.float64(fy), np.complex128(c)
+        screen = screen + c * np.exp(1j * 2 * np.pi * (fx * x + fy * y))
+    return screen - np.mean(screen)
 
 
 # --------------------------------------------------------------------------------------------------

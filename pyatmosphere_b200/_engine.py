@@ -193,7 +193,11 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
         raise ValueError(f"at most {nat.MAX_PUPILS} fixed and {nat.MAX_PUPILS} tracked apertures per simulation")
     cols = table_columns(pupils_fixed, pupils_tracked)
     # numpy mode: every rank draws the whole batch so that the global RNG stream stays identical on all ranks
-    host = draw_spectra_numpy(path, count) if gpu.config["rng"] == "numpy" else None
+    device_rng = gpu.config["rng"] != "numpy"
+    if device_rng and not all(getattr(ps, "device_rng", False) for ps in path.phase_screens):
+        raise ValueError("gpu.config['rng'] = 'philox' draws sparse-spectrum coefficients with fixed ring powers "
+                         "(SSPhaseScreen); use rng = 'numpy' for the other screen generators")
+    host = None if device_rng else draw_spectra_numpy(path, count)
     B = len(mine)
     if B == 0:
         return np.zeros((0, len(cols)), dtype=np.float64)

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pa_source_gaussian": (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _vp]),
     "pa_vacuum_leg": (_int, [_vp, _vp, _int, _dbl, _dbl, _vp]),
     "pa_screen_ss": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _dbl, _dbl, _int, _vp, _vp, _int, _int, _dbl, _vp]),
+    "pa_screen_fft": (_int, [_vp, _vp, _int, _vp, _int, _vp, _vp, _vp]),
     "pa_apply_screen": (_int, [_vp, _vp, _int, _vp, _dbl, _vp]),
     "pa_phase_to_turns": (_int, [_vp, _vp, _int, _vp, _sz, _vp]),
     "pa_intensity": (_int, [_vp, _vp, _vp, _int, _vp]),

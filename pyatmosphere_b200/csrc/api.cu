@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "fft_core.cuh"
 #include "internal.h"
+#include "internal_fftscreen.h"
 #include "internal_measure.h"
 #include "internal_rng.h"
 #include "internal_screen.h"
@@ -94,6 +95,8 @@ struct pa_ctx {
     double* rowsums = nullptr; size_t rowsums_bytes = 0;   // per-row sums of the fused final pass
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
+    int* perm_dev = nullptr;                              // device copy of `perm` (FFT phase screens)
+    void* fftws = nullptr; size_t fftws_bytes = 0;        // subharmonic tables and mean partials of the FFT phase screens
     int num_sms = 148;
     size_t csize() const { return prec == 0 ? 8 : 16; }
     size_t rsize() const { return prec == 0 ? 4 : 8; }
@@ -578,7 +581,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
 int pa_ctx_destroy(pa_ctx* c) {
     if (!c) return PA_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->x, c->y, c->tw, c->tw_sub, c->otw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums};
+    void* ptrs[] = {c->x, c->y, c->tw, c->tw_sub, c->otw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums, c->perm_dev, c->fftws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& h : c->htabs) {
@@ -656,6 +659,67 @@ int pa_screen_ss(pa_ctx* c, const float* fx, const float* fy, const float* coef,
     if (rc) return rc;
     return screens(c, fx, fy, coef, m, m_split, degree, shift_x, shift_y, nscreens, turns, phi, phi_f64, method, coef_bound,
                    (cudaStream_t)stream);
+}
+
+int pa_screen_fft(pa_ctx* c, const void* spectrum, int nscreens, const double* terms_host, int nterms, void* out_complex,
+                  void* out_real, void* stream) {
+    PA_REQUIRE(c && spectrum && nscreens > 0 && nterms >= 0 && (nterms == 0 || terms_host), "bad arguments to pa_screen_fft");
+    PA_REQUIRE(out_complex || out_real, "pa_screen_fft needs at least one output");
+    PA_REQUIRE(c->axes_set, "pa_ctx_set_axes must be called before pa_screen_fft");
+    PA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = c->n;
+    const size_t plane = (size_t)n * n;
+    int rc = grow(&c->field, &c->field_bytes, (size_t)nscreens * plane * c->csize());
+    if (rc) return rc;
+    if (!c->perm_dev) {
+        PA_CUDA(cudaMalloc((void**)&c->perm_dev, (size_t)n * sizeof(int)));
+        PA_CUDA(cudaMemcpy(c->perm_dev, c->perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    // workspace layout (doubles): terms | ex | ey | partials | rowsum
+    const size_t per_row = (size_t)(n + 255) / 256;
+    const size_t n_terms = (size_t)nscreens * nterms * 4, n_tab = (size_t)nscreens * nterms * n * 2;
+    const size_t n_part = (size_t)nscreens * n * per_row * 2, n_rows = (size_t)nscreens * n * 2;
+    rc = grow(&c->fftws, &c->fftws_bytes, (n_terms + 2 * n_tab + n_part + n_rows + 8) * sizeof(double));
+    if (rc) return rc;
+    double* w = (double*)c->fftws;
+    FftScreenLaunch a;
+    a.n = n;
+    a.nscreens = nscreens;
+    a.spectrum = spectrum;
+    a.ws = c->field;
+    a.perm = c->perm_dev;
+    a.terms = w;
+    a.nterms = nterms;
+    a.x = c->x;
+    a.y = c->y;
+    a.ex = (double2*)(w + ((n_terms + 1) & ~(size_t)1));
+    a.ey = a.ex + n_tab / 2;
+    a.partials = a.ey + n_tab / 2;
+    a.rowsum = a.partials + n_part / 2;
+    a.out_complex = out_complex;
+    a.out_real = out_real;
+    if (nterms > 0) PA_CUDA(cudaMemcpyAsync(w, terms_host, n_terms * sizeof(double), cudaMemcpyHostToDevice, st));
+    note(1);
+    rc = check_launch(launch_fftscreen_gather(c->prec, a, st), "FFT screen gather");
+    if (rc) return rc;
+    ColLaunch cl;                       // IFFT_y of every column (direct kernel, storage order in, natural out)
+    cl.field = c->field;
+    cl.tw = c->tw;
+    cl.hp = nullptr;
+    cl.alpha_re = 1.0;
+    cl.alpha_im = 0.0;
+    cl.batch = nscreens;
+    cl.tmap = nullptr;
+    cl.num_sms = c->num_sms;
+    cl.inv_only = true;
+    note(1);
+    rc = check_launch(launch_cols(c->prec, n, cl, st), "FFT screen column pass");
+    if (rc) return rc;
+    rc = rows(c, c->field, nscreens, true, false, false, nullptr, 1.0, 0, 0, 0, st);     // IFFT_x of every row
+    if (rc) return rc;
+    note(fftscreen_finish_launches(a));
+    return check_launch(launch_fftscreen_finish(c->prec, a, st), "FFT screen finish");
 }
 
 int pa_apply_screen(pa_ctx* c, void* field, int batch, const void* turns, double scale, void* stream) {

@@ -6,6 +6,8 @@
 //   k_rows : per row   [source | load natural | load permuted -> IFFT_x] -> [* scale * exp(-2 pi i turns)]
 //                      -> [FFT_x -> store permuted | store natural]
 //   k_cols : per column  load -> FFT_y -> * H(ky,kx) -> IFFT_y -> store      (always in place)
+//            INV_ONLY: load a column spectrum (storage order) -> * real scale -> IFFT_y -> store natural; with a
+//            k_rows<IN_PERM, !OUT_PERM> launch this is a plain inverse 2-D DFT (FFT phase screens, screen_fft.cu)
 //
 // One vacuum leg = FFT_x, (FFT_y, H, IFFT_y), IFFT_x; the trailing IFFT_x of a leg, the screen multiply and
 // the leading FFT_x of the next leg run in ONE k_rows launch, so a steady-state split-step stage is two
@@ -259,7 +261,7 @@ template <typename T> struct ColArgs {
 
 // One CTA = TC adjacent columns of one field, N/E threads per column; thread index = c + TC * t so that a warp
 // touches TC*sizeof(C)-byte segments of 32/TC consecutive rows.
-template <typename T, int N, int E, int TC>
+template <typename T, int N, int E, int TC, bool INV_ONLY = false>
 __global__ void __launch_bounds__(TC * (N / E)) k_cols(ColArgs<T> a) {
     using C = cplx<T>;
     constexpr int L = plan_len(N, E);
@@ -271,6 +273,14 @@ __global__ void __launch_bounds__(TC * (N / E)) k_cols(ColArgs<T> a) {
     C* ptr = a.field + (size_t)blockIdx.y * N * N + col;
     const ColAddr<N, E, TC> addr{c};
     C v[E];
+    if constexpr (INV_ONLY) {
+#pragma unroll
+        for (int i = 0; i < E; ++i) {
+            v[i] = ptr[(size_t)io_pos<N, E>(t, i) * N];
+            v[i].x *= a.alpha_re;
+            v[i].y *= a.alpha_re;
+        }
+    } else {
 #pragma unroll
     for (int i = 0; i < E; ++i) v[i] = ptr[(size_t)reg_pos<N, E, 0>(t, i) * N];
 
@@ -283,6 +293,7 @@ __global__ void __launch_bounds__(TC * (N / E)) k_cols(ColArgs<T> a) {
             const C h = cmul(ldg_c<T>(a.hp + io_pos<N, E>(t, i)), hx);     // register (t,i) holds storage index t + i*T
             v[i] = cmul(v[i], h);
         }
+    }
     }
 
     fft_inv<T, N, E>(v, t, sm, addr, a.tw);

@@ -44,6 +44,8 @@ struct ColLaunch {
     const void* hpy = nullptr;      // ky factors in the composite order of the split transform
     const void* tw_sub = nullptr;   // stage twiddles of the inner (n / 32)-point plan
     const void* otw = nullptr;      // outer-stage twiddles exp(-2 pi i t j / n), [n / 32][32]
+    // inverse-only pass (direct kernel): column spectra in storage order -> alpha_re * IFFT_y, natural order out
+    bool inv_only = false;
 };
 
 // implemented once per grid size in fft_n<N>.cu; return cudaError_t as int, or -1 for an unsupported size

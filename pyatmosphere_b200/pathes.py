@@ -93,7 +93,7 @@ class PhaseScreensPath(AbstractPath):
         return eng.PathDescriptor(legs, scales, final, src.wvl, getattr(src, "w0", 1.0), getattr(src, "F0", np.inf),
                                   ps.f_grid.points, m_split, degree, shift,
                                   eng.screen_method(self.channel.grid.resolution[0]), from_field,
-                                  coef_bound=max(eng.coef_bound(q._get_psd(), m_split) for q in self.phase_screens))
+                                  coef_bound=max(eng.coef_bound(q._ring_power(), m_split) for q in self.phase_screens))
 
     def _draw_spectra(self, wind):
         """Spectra of all screens in path order -- the order in which the reference's generator draws them."""
@@ -120,9 +120,11 @@ class PhaseScreensPath(AbstractPath):
         return DeviceArray(field[0])
 
     def _fusable(self):
-        from .phase_screens import SSPhaseScreen
+        """The fused propagator synthesises every screen itself from (fx, fy, c): it serves paths whose screens are all
+        sums of harmonics over one shared log-polar grid (SSPhaseScreen, SUPhaseScreen)."""
+        from .phase_screens import HarmonicSumScreen
         ps = self.phase_screens
-        return len(ps) > 0 and all(isinstance(p, SSPhaseScreen) and p.f_grid is ps[0].f_grid for p in ps)
+        return len(ps) > 0 and all(isinstance(p, HarmonicSumScreen) and p.f_grid is ps[0].f_grid for p in ps)
 
     def lossless_output(self, input, *args, **kwargs):
         if self._fusable() and not args:
@@ -152,8 +154,15 @@ class PhaseScreensPath(AbstractPath):
         scales = eng.path_losses(self, legs)
         for i, phase_screen in enumerate(self.phase_screens):
             nat.check(lib.pa_vacuum_leg(h, nat.ptr(field), 1, float(legs[i]), wvl, nat.stream_ptr()))
-            spectrum = phase_screen._get_spectrum(use_cached_spectrum=wind)
-            turns, phi = phase_screen._synthesize(spectrum, shift, want_turns=True, want_phi=True)
+            if hasattr(phase_screen, "_synthesize"):
+                spectrum = phase_screen._get_spectrum(use_cached_spectrum=wind)
+                turns, phi = phase_screen._synthesize(spectrum, shift, want_turns=True, want_phi=True)
+            else:
+                # any other generator (FFTPhaseScreen): the real phase as the screen returns it, reduced to turns
+                phi = phase_screen.generate(*args, **kwargs).t.to(ctx.rdtype).contiguous()
+                turns = nat.torch_mod().empty_like(phi)
+                nat.check(lib.pa_phase_to_turns(h, nat.ptr(phi), 1 if ctx.precision == nat.PA_C128 else 0, nat.ptr(turns),
+                                                phi.numel(), nat.stream_ptr()))
             nat.check(lib.pa_apply_screen(h, nat.ptr(field), 1, nat.ptr(turns), float(scales[i]), nat.stream_ptr()))
             yield DeviceArray(field[0].clone()), DeviceArray(phi)
         nat.check(lib.pa_vacuum_leg(h, nat.ptr(field), 1, float(legs[-1]), wvl, nat.stream_ptr()))

@@ -217,3 +217,62 @@ def test_two_rank_gloo_reduction():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "OK" in o, o
+
+
+# ---- the other screen generators (host side only: draws, bounds, routing) ------------------------------------------
+def _n4_channel(screen, n=128, count=2):
+    return pa.Channel(grid=pa.RectGrid(resolution=n, delta=4e-3), source=pa.GaussianSource(wvl=808e-9, w0=0.06, F0=np.inf),
+                      path=pa.IdenticalPhaseScreensPath(phase_screen=screen, length=6e3, count=count),
+                      pupil=pa.CirclePupil(radius=0.1))
+
+
+def test_su_screen_draws_match_oracle_and_reference():
+    g = load_golden("su128")
+    p = g["params"]
+    ch = _n4_channel(pa.SUPhaseScreen(model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
+                                      f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])))
+    ch.path.init_phase_screens()
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    np.random.seed(int(g["seed"]))
+    mine = [ps._get_spectrum(False) for ps in ch.path.phase_screens]
+    np.random.seed(int(g["seed"]))
+    for sp in mine:
+        rho, theta, value = orc.draw_su_spectrum(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+        assert np.array_equal(sp.rho, rho) and np.array_equal(sp.theta, theta)
+        assert sp.value.dtype == np.complex64 and np.array_equal(sp.value, value)
+    # the per-ring power handed to the planner bounds E|c|^2/2 at every admissible radius, here at the drawn ones
+    ps = ch.path.phase_screens[0]
+    power = ps._ring_power()
+    dens = orc.psd_phi_f(mine[0].rho.astype(np.float64), p["Cn2"], p["l0"], p["L0"], 2 * np.pi / p["wvl"], ps.thickness)
+    assert np.all(power >= dens * np.pi * orc.su_delta_k(base).astype(np.float64))
+    assert np.array_equal(ps.delta_k_base, orc.su_delta_k(base))
+    # routing: SU screens over one shared log-polar grid go through the fused propagator, but not the device RNG
+    assert ch.path._fusable() and not ps.device_rng and pa.SSPhaseScreen.device_rng
+    m_split, degree = ps.low_ring_plan()
+    assert 0 <= m_split < p["m"] and degree <= eng.MAX_DEGREE
+
+
+def test_fft_screen_draws_match_oracle():
+    g = load_golden("fft128")
+    p = g["params"]
+    ch = _n4_channel(pa.FFTPhaseScreen(p["subharmonics"], model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])), n=p["n"])
+    ch.path.init_phase_screens()
+    assert not ch.path._fusable()
+    np.random.seed(int(g["seed"]))
+    cn, terms = ch.path.phase_screens[0]._draw()
+    np.random.seed(int(g["seed"]))
+    cn_o, terms_o = orc.draw_fft_screen(p["n"], p["delta"], p["subharmonics"], p["Cn2"], p["l0"], p["L0"], p["wvl"],
+                                        p["length"] / p["count"])
+    assert cn.dtype == np.complex128 and np.array_equal(cn, cn_o)
+    assert np.allclose(cn[:8, :8], g["cn0_corner"], rtol=1e-14, atol=0)
+    live = [(fx, fy, c) for fx, fy, c in terms_o if c != 0]
+    assert terms.shape == (8 * p["subharmonics"], 4) and len(live) == len(terms)
+    for row, (fx, fy, c) in zip(terms, live):
+        assert row[0] == fx and row[1] == fy and complex(row[2], row[3]) == c
+
+
+def test_andrews_model_matches_oracle():
+    m = pa.AndrewsModel(Cn2=3e-15, l0=4e-3, L0=50.0)
+    kappa = np.geomspace(1e-3, 5e3, 64)
+    assert np.array_equal(m.psd_n(kappa), orc.andrews_psd_n(kappa, 3e-15, 4e-3, 50.0))
+    assert np.array_equal(m.psd_phi_f(kappa, 7.7e6, 300.0), orc.psd_phi_f(kappa, 3e-15, 4e-3, 50.0, 7.7e6, 300.0, orc.andrews_psd_n))

@@ -218,3 +218,92 @@ def test_time_series_replay():
         out, legs = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", keep_legs=True, through_output=False)
         got = [abs(u[c, c]) ** 2 for u in legs] + [abs(out[c, c]) ** 2]
         assert np.allclose(got, g["i0"][it], rtol=2e-5)
+
+
+# ---- the other screen generators ----------------------------------------------------------
+def _su_screens(g, mode):
+    p = g["params"]
+    x, y = _axes(p)
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    np.random.seed(int(g["seed"]))
+    out = []
+    for _ in range(p["count"]):
+        rho, theta, value = orc.draw_su_spectrum(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+        assert value.dtype == np.complex64
+        fx, fy = orc.spectrum_to_fxy(rho, theta)
+        out.append(orc.ss_screen(x, y, fx, fy, value, mode=mode, diag_product=True))
+    return out
+
+
+def test_su_screens_and_field_equal_reference():
+    """SUPhaseScreen (phase_screens.py:154-179): same draw order as the sparse-spectrum screen, coefficients sampled
+    from the spectrum at the drawn radius; contraction identical to SSPhaseScreen's."""
+    g = load_golden("su128")
+    p = g["params"]
+    x, y = _axes(p)
+    screens = _su_screens(g, "ref")
+    for s, phi in enumerate(screens):
+        assert phi.dtype == np.float32
+        assert np.max(np.abs(phi - g["screens"][s])) <= 2e-6 * np.max(np.abs(phi)) + 1e-6
+    pos = orc.screen_positions(p["length"], p["count"])
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="ref")
+    out, legs = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", keep_legs=True)
+    assert rel_l2(out, g["field"]) < 2e-6
+    for a, b in zip(legs, g["legs"]):
+        assert rel_l2(a, b) < 2e-6
+    s64 = _su_screens(g, "f64")
+    for s, phi in enumerate(s64):
+        assert np.max(np.abs(phi - g["screens"][s])) < 5e-3
+
+
+def _fft_draws(g):
+    p = g["params"]
+    np.random.seed(int(g["seed"]))
+    return [orc.draw_fft_screen(p["n"], p["delta"], p["subharmonics"], p["Cn2"], p["l0"], p["L0"], p["wvl"],
+                                p["length"] / p["count"]) for _ in range(p["count"])]
+
+
+def test_fft_screens_and_field_equal_reference():
+    """FFTPhaseScreen (phase_screens.py:37-67): draw order (main grid, then one 3x3 patch per subharmonic level; real
+    normals before imaginary), centred inverse transform, subharmonic sum, mean removal."""
+    g = load_golden("fft128")
+    p = g["params"]
+    x, y = _axes(p)
+    draws = _fft_draws(g)
+    cn0 = draws[0][0]
+    assert str(cn0.dtype) == str(g["cn0_dtype"]) == "complex128"
+    assert np.allclose(cn0[:8, :8], g["cn0_corner"], rtol=1e-14, atol=0)
+    assert np.allclose([cn0.sum(), np.abs(cn0).sum()], g["cn0_checksum"], rtol=1e-12)
+    assert cn0[p["n"] // 2, p["n"] // 2] == 0
+    assert len(draws[0][1]) == 9 * p["subharmonics"]
+    full0 = orc.fft_screen(cn0, draws[0][1], x, y, mode="ref")
+    assert rel_l2(full0, g["screen0_complex"]) < 1e-13
+    assert abs(full0.mean()) < 1e-12 * np.abs(full0).max()
+    screens = []
+    for s, (cn, terms) in enumerate(draws):
+        for mode in ("ref", "f64"):
+            phi = orc.fft_screen(cn, terms, x, y, mode=mode).real
+            assert rel_l2(phi, g["screens"][s]) < 1e-13
+        screens.append(phi)
+    pos = orc.screen_positions(p["length"], p["count"])
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="ref")
+    out, legs = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref", keep_legs=True)
+    assert rel_l2(out, g["field"]) < 2e-6
+    for a, b in zip(legs, g["legs"]):
+        assert rel_l2(a, b) < 2e-6
+
+
+def test_fft_screen_matches_direct_sum():
+    """The centred inverse transform of the oracle against the defining sum  sum_pq cn[p,q] exp(2 pi i (i' p' + j' q')/N)
+    on a small odd-free case, plus linearity in the coefficients (size-independent property used on the GPU too)."""
+    n = 16
+    rng = np.random.default_rng(3)
+    cn = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    idx = np.arange(n) - n // 2
+    e = np.exp(2j * np.pi * np.outer(idx, idx) / n)
+    direct = e @ cn @ e.T
+    x, y = orc.rect_xy(n, 1.0)
+    got = orc.fft_screen(cn, [], x, y, mode="f64")
+    assert rel_l2(got, direct - direct.mean()) < 1e-13
+    a = orc.fft_screen(2 * cn, [], x, y, mode="f64")
+    assert rel_l2(a, 2 * got) < 1e-14
