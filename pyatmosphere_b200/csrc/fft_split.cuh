@@ -10,6 +10,8 @@
 // columns] tiles (256-byte row segments), with the transfer-function factor indexed in the composite order
 // storage row M j + s  <->  frequency j + R0 * perm_M[s].  The inverse outer stage streams the field once more.
 // Three sweeps instead of one, each at streaming speed, against 8-byte accesses in the single-column kernel.
+// complex128 uses the same factorisation (32 x 256, 16-column tiles of 256 rows; the 32 double-precision values of the
+// outer butterfly take 128 registers, so that kernel runs one CTA of 256 threads per SM partition less).
 #pragma once
 #include "fft_core.cuh"
 
@@ -68,7 +70,7 @@ template <typename T> __device__ __forceinline__ void dft32_inv(cplx<T> (&v)[32]
 // Outer stage of the split column transform, in place.  grid = (N / 256, M, batch), 256 threads = 256 adjacent
 // columns; otw[t * 32 + j] = exp(-2 pi i t j / N).
 template <typename T, int N, bool INV>
-__global__ void __launch_bounds__(256, 2) k_col_outer(cplx<T>* __restrict__ field, const cplx<T>* __restrict__ otw) {
+__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) k_col_outer(cplx<T>* __restrict__ field, const cplx<T>* __restrict__ otw) {
     using C = cplx<T>;
     constexpr int R0 = 32, M = N / R0;
     const int t = blockIdx.y;
