@@ -533,3 +533,32 @@ def test_split_column_pass_random_field_8192(dtype):
     out = ch.path.output(DeviceArray(torch.as_tensor(u).cuda())).get()
     want = orc.vacuum_leg(u, length, wvl, delta, mode="f64")
     assert rel_l2(out, want) < (2e-6 if dtype == "complex64" else 1e-12)
+
+
+def test_monte_carlo_statistics_match_reference_notebook():
+    """The reference's recorded Monte-Carlo run (main.ipynb cells 15-16: README QuickChannel, 2000 samples):
+        sigma_BW_x = 3.9e-02 +- 6.2e-04,  sigma_LT_x = 1.8e-01 +- 6.8e-04,  W_ST = 1.6e-01 +- 4.3e-04
+    reproduced within Monte-Carlo error by 2000 device-RNG realizations (tensor-core screens, fused statistics).
+    Tolerance: 4 combined standard errors plus half a unit of the last printed digit.  The transmittance sample of
+    the device RNG is also compared with a host-RNG sample (reference draw order) by a two-sample KS test."""
+    from scipy import stats
+    pa = _pa("complex64", screen_method="auto", theta_cut=None, rng="philox", seed=2021, batch=16)
+    ch = pa.QuickChannel(Cn2=1e-15, length=10000, count_ps=5, beam_w0=0.09, beam_wvl=8.08e-07, aperture_radius=0.12)
+    beam = pa.simulations.BeamResult(ch, max_size=2000)
+    pdt = pa.simulations.PDTResult(ch, max_size=2000)
+    pa.simulations.Simulation([beam, pdt]).run()
+    assert len(beam.measures[0]) == 2000 and len(pdt.measures[0]) == 2000
+    recorded = {"bw": (3.9e-2, 6.2e-4, 0.05e-2), "lt": (1.8e-1, 6.8e-4, 0.05e-1), "st": (1.6e-1, 4.3e-4, 0.05e-1)}
+    for key, (ref, ref_err, half_digit) in recorded.items():
+        val, err = getattr(beam, key)
+        assert abs(val - ref) < 4 * np.hypot(err, ref_err) + half_digit, (key, val, err)
+        assert 0.5 * ref_err < err < 2 * ref_err, (key, err)              # same sample size -> same error bar
+    eta_dev = np.asarray(pdt.measures[0].data)
+    assert np.all((eta_dev > 0) & (eta_dev < 1))
+    pa.gpu.config.update(rng="numpy", batch=16)
+    ch2 = pa.QuickChannel(Cn2=1e-15, length=10000, count_ps=5, beam_w0=0.09, beam_wvl=8.08e-07, aperture_radius=0.12)
+    pdt2 = pa.simulations.PDTResult(ch2, max_size=320)
+    np.random.seed(99)
+    pa.simulations.Simulation([pdt2]).run()
+    eta_host = np.asarray(pdt2.measures[0].data)
+    assert stats.ks_2samp(eta_dev, eta_host).pvalue > 1e-3
