@@ -244,7 +244,7 @@ __device__ __forceinline__ void smem_get(cplx<T> (&v)[E], int t, const cplx<T>* 
 template <typename T, int N, int E, int SA, int SB, typename Addr>
 __device__ __forceinline__ void exchange(cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
     smem_put<T, N, E, SA>(v, t, sm, addr);
-    __syncthreads();
+    addr.sync();
     smem_get<T, N, E, SB>(v, t, sm, addr);
 }
 

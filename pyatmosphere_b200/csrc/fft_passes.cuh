@@ -56,15 +56,32 @@ template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
     }
 }
 
+// `sync()` is the barrier of one exchange.  The rows of a CTA are independent transforms in private shared-memory
+// regions, so when a row is made of whole warps its N/E threads synchronise on a named barrier of their own (id 1 + row
+// in CTA) and the rows of a CTA drift apart instead of all waiting for the slowest warp of the block.
 template <int N, int E> struct RowAddr {
     static constexpr bool kContiguous = true;
+    static constexpr int TPF = N / E;
     int base;
     __device__ __forceinline__ int operator()(int p) const { return base + swz_row<N, E>(p); }
+    __device__ __forceinline__ void sync() const {
+#ifndef PA_ROW_BLOCK_BARRIER
+        if constexpr (TPF % 32 == 0) {
+            const int row_in_cta = base / N;
+            if (row_in_cta < 15) {
+                asm volatile("bar.sync %0, %1;" ::"r"(row_in_cta + 1), "n"(TPF) : "memory");
+                return;
+            }
+        }
+#endif
+        __syncthreads();
+    }
 };
 template <int N, int E, int TC> struct ColAddr {
     static constexpr bool kContiguous = false;
     int c;
     __device__ __forceinline__ int operator()(int p) const { return swz_col<N, E, TC>(p) * TC + c; }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
 // exp(-2 pi i t) for t in turns.  float: MUFU sin/cos (|abs err| < 4e-7 on [-pi, pi]); double: sincospi.
