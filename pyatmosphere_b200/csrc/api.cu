@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <complex>
 #include <vector>
@@ -676,11 +677,39 @@ int pa_screen_fft(pa_ctx* c, const void* spectrum, int nscreens, const double* t
         PA_CUDA(cudaMalloc((void**)&c->perm_dev, (size_t)n * sizeof(int)));
         PA_CUDA(cudaMemcpy(c->perm_dev, c->perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
     }
-    // workspace layout (doubles): terms | ex | ey | partials | rowsum
+    // group the terms of every screen by their x-frequency (see screen_fft.cu): stable order of first appearance
+    std::vector<double> sorted((size_t)nscreens * nterms * 4);
+    std::vector<std::vector<int>> offs(nscreens);
+    int ngroups = 0;
+    for (int b = 0; b < nscreens; ++b) {
+        const double* tb = terms_host + (size_t)b * nterms * 4;
+        std::vector<double> keys;
+        std::vector<std::vector<int>> members;
+        for (int t = 0; t < nterms; ++t) {
+            size_t g = 0;
+            while (g < keys.size() && keys[g] != tb[t * 4]) ++g;
+            if (g == keys.size()) {
+                keys.push_back(tb[t * 4]);
+                members.emplace_back();
+            }
+            members[g].push_back(t);
+        }
+        int at = 0;
+        offs[b].push_back(0);
+        for (const auto& m : members) {
+            for (int t : m) memcpy(&sorted[((size_t)b * nterms + at++) * 4], tb + t * 4, 4 * sizeof(double));
+            offs[b].push_back(at);
+        }
+        ngroups = std::max(ngroups, (int)members.size());
+    }
+    std::vector<int> goff((size_t)nscreens * (ngroups + 1));
+    for (int b = 0; b < nscreens; ++b)
+        for (int g = 0; g <= ngroups; ++g) goff[(size_t)b * (ngroups + 1) + g] = offs[b][std::min<size_t>(g, offs[b].size() - 1)];
+    // workspace layout (doubles): terms | ex | gy | partials | rowsum | group offsets (ints)
     const size_t per_row = (size_t)(n + 255) / 256;
-    const size_t n_terms = (size_t)nscreens * nterms * 4, n_tab = (size_t)nscreens * nterms * n * 2;
+    const size_t n_terms = (size_t)nscreens * nterms * 4, n_tab = (size_t)nscreens * ngroups * n * 2;
     const size_t n_part = (size_t)nscreens * n * per_row * 2, n_rows = (size_t)nscreens * n * 2;
-    rc = grow(&c->fftws, &c->fftws_bytes, (n_terms + 2 * n_tab + n_part + n_rows + 8) * sizeof(double));
+    rc = grow(&c->fftws, &c->fftws_bytes, (n_terms + 2 * n_tab + n_part + n_rows + 8) * sizeof(double) + goff.size() * sizeof(int));
     if (rc) return rc;
     double* w = (double*)c->fftws;
     FftScreenLaunch a;
@@ -691,15 +720,22 @@ int pa_screen_fft(pa_ctx* c, const void* spectrum, int nscreens, const double* t
     a.perm = c->perm_dev;
     a.terms = w;
     a.nterms = nterms;
+    a.ngroups = ngroups;
     a.x = c->x;
     a.y = c->y;
     a.ex = (double2*)(w + ((n_terms + 1) & ~(size_t)1));
     a.ey = a.ex + n_tab / 2;
     a.partials = a.ey + n_tab / 2;
     a.rowsum = a.partials + n_part / 2;
+    int* goff_dev = (int*)(a.rowsum + n_rows / 2);
+    a.goff = goff_dev;
     a.out_complex = out_complex;
     a.out_real = out_real;
-    if (nterms > 0) PA_CUDA(cudaMemcpyAsync(w, terms_host, n_terms * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (nterms > 0) {
+        PA_CUDA(cudaStreamSynchronize(st));      // an earlier call on this stream may still be reading the term tables
+        PA_CUDA(cudaMemcpy(goff_dev, goff.data(), goff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    if (nterms > 0) PA_CUDA(cudaMemcpy(w, sorted.data(), n_terms * sizeof(double), cudaMemcpyHostToDevice));
     note(1);
     rc = check_launch(launch_fftscreen_gather(c->prec, a, st), "FFT screen gather");
     if (rc) return rc;

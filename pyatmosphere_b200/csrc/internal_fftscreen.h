@@ -9,14 +9,16 @@ struct FftScreenLaunch {
     const void* spectrum;   // [nscreens][n][n] complex, centred frequency order (index n/2 = zero frequency)
     void* ws;               // [nscreens][n][n] complex workspace: spectrum in storage order, then the transform
     const int* perm;        // [n] frequency held at storage position p (pa_ctx_permutation), device copy
-    const double* terms;    // [nscreens][nterms][4] {fx, fy, re c, im c}, device; may be null when nterms == 0
+    const double* terms;    // [nscreens][nterms][4] {fx, fy, re c, im c}, device, sorted by group; may be null when nterms == 0
     int nterms;
+    const int* goff;        // [nscreens][ngroups + 1] first term of every group of equal fx (device)
+    int ngroups;
     const float* x;         // float32 axes of the context
     const float* y;
-    double2* ex;            // workspace [nscreens][nterms][n]
-    double2* ey;            // workspace [nscreens][nterms][n]
+    double2* ex;            // workspace [nscreens][ngroups][n]
+    double2* ey;            // workspace [nscreens][ngroups][n]
     double2* partials;      // workspace [nscreens][n][ceil(n / 256)]
-    double2* rowsum;        // workspace [nscreens][n]
+    double2* rowsum;        // workspace: mean of every screen ([nscreens] used)
     void* out_complex;      // [nscreens][n][n] complex or null
     void* out_real;         // [nscreens][n][n] real or null
 };

@@ -6,7 +6,7 @@
 // inverse DFT of  Y[p][q] = (-1)^(p+q) cn[(p + N/2) % N][(q + N/2) % N].  The transform itself is the inverse half
 // of the split-step passes (k_cols<INV_ONLY> + k_rows<IN_PERM, !OUT_PERM>, fft_passes.cuh); this file holds the
 // kernels around it: the gather of the centred spectrum into spectrum storage order, the subharmonic tables, the
-// sum + mean reduction, and the final centring.
+// sum + mean reduction, and the final centring (7 launches per batch of screens).
 #include "common.cuh"
 #include "internal_fftscreen.h"
 
@@ -33,20 +33,31 @@ __global__ void __launch_bounds__(kGatherThreads) k_fftscreen_gather(const cplx<
     ws[plane + (size_t)py * n + px] = v;
 }
 
-// EX[b][t][j] = exp(2 pi i fx_t x_j),  EY[b][t][i] = c_t exp(2 pi i fy_t y_i); terms[b][t] = {fx, fy, re c, im c}.
+// The terms of a screen are grouped by their x-frequency (the host sorts them: terms[b][goff[b][g] .. goff[b][g+1]) share
+// fx), because  sum_t c_t e^{2 pi i (fx_t x + fy_t y)} = sum_g e^{2 pi i fx_g x} G_g(y),  G_g(y) = sum_{t in g} c_t e^{2 pi i fy_t y}:
+// a 3 x 3 subharmonic patch costs 3 complex multiply-adds per pixel instead of 8.
+//   EX[b][g][j] = exp(2 pi i fx_g x_j),   GY[b][g][i] = G_g(y_i);   terms[b][t] = {fx, fy, re c, im c}.
 // The reference forms f*x + f*y in float32 (phase_screens.py:63-65); here the float32 axes are promoted exactly and
 // the phase is evaluated in float64 (the float64 oracle's definition).
-__global__ void k_fftscreen_tables(const double* __restrict__ terms, int nterms, const float* __restrict__ x,
-                                   const float* __restrict__ y, int n, double2* __restrict__ ex, double2* __restrict__ ey) {
+__global__ void k_fftscreen_tables(const double* __restrict__ terms, const int* __restrict__ goff, int nterms, int ngroups,
+                                   const float* __restrict__ x, const float* __restrict__ y, int n, double2* __restrict__ ex,
+                                   double2* __restrict__ gy) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int t = blockIdx.y, b = blockIdx.z;
+    const int g = blockIdx.y, b = blockIdx.z;
     if (j >= n) return;
-    const double* tm = terms + ((size_t)b * nterms + t) * 4;
+    const int t0 = goff[b * (ngroups + 1) + g], t1 = goff[b * (ngroups + 1) + g + 1];
+    const double* tm = terms + (size_t)b * nterms * 4;
     double s, c;
-    sincospi(2.0 * tm[0] * (double)x[j], &s, &c);
-    ex[((size_t)b * nterms + t) * n + j] = make_double2(c, s);
-    sincospi(2.0 * tm[1] * (double)y[j], &s, &c);
-    ey[((size_t)b * nterms + t) * n + j] = make_double2(tm[2] * c - tm[3] * s, tm[2] * s + tm[3] * c);
+    sincospi(2.0 * (t0 < t1 ? tm[t0 * 4] : 0.0) * (double)x[j], &s, &c);
+    ex[((size_t)b * ngroups + g) * n + j] = make_double2(c, s);
+    const double yv = (double)y[j];
+    double re = 0.0, im = 0.0;
+    for (int t = t0; t < t1; ++t) {
+        sincospi(2.0 * tm[t * 4 + 1] * yv, &s, &c);
+        re += tm[t * 4 + 2] * c - tm[t * 4 + 3] * s;
+        im += tm[t * 4 + 2] * s + tm[t * 4 + 3] * c;
+    }
+    gy[((size_t)b * ngroups + g) * n + j] = make_double2(re, im);
 }
 
 // out = ws + subharmonics; per-block sums of the result (float64) for the mean.  One block = kAddThreads columns
@@ -91,45 +102,44 @@ __global__ void __launch_bounds__(kAddThreads) k_fftscreen_add(cplx<T>* __restri
     }
 }
 
-// row sums of the block partials in a fixed order -> rowsum[b][i]
-__global__ void k_fftscreen_rowsum(const double2* __restrict__ partials, int per_row, int n, double2* __restrict__ rowsum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
-    if (i >= n) return;
+// mean[b] = (sum of all block partials of screen b) / n^2, folded in a fixed order by ONE block per screen: thread k
+// sums the partials of rows k, k + 1024, ... and a shared-memory tree adds the 1024 thread sums -> deterministic.
+constexpr int kMeanThreads = 1024;
+__global__ void __launch_bounds__(kMeanThreads) k_fftscreen_mean(const double2* __restrict__ partials, int per_row, int n,
+                                                                  double2* __restrict__ mean) {
+    __shared__ double sre[kMeanThreads], sim[kMeanThreads];
+    const int b = blockIdx.x;
     double r = 0.0, q = 0.0;
-    for (int k = 0; k < per_row; ++k) {
-        const double2 p = partials[((size_t)b * n + i) * per_row + k];
-        r += p.x;
-        q += p.y;
-    }
-    rowsum[(size_t)b * n + i] = make_double2(r, q);
-}
-
-// subtract the mean (every block folds the n row sums in the same order -> deterministic) and write the outputs
-template <typename T>
-__global__ void __launch_bounds__(kAddThreads) k_fftscreen_center(const cplx<T>* __restrict__ ws, const double2* __restrict__ rowsum,
-                                                                   int n, cplx<T>* __restrict__ out_c, T* __restrict__ out_re) {
-    __shared__ double2 mean_s;
-    const int b = blockIdx.z;
-    if (threadIdx.x < 32) {
-        double r = 0.0, q = 0.0;
-        for (int k = threadIdx.x; k < n; k += 32) {
-            const double2 p = rowsum[(size_t)b * n + k];
+    for (int i = threadIdx.x; i < n; i += kMeanThreads)
+        for (int k = 0; k < per_row; ++k) {
+            const double2 p = partials[((size_t)b * n + i) * per_row + k];
             r += p.x;
             q += p.y;
         }
-        for (int o = 16; o > 0; o >>= 1) {
-            r += __shfl_xor_sync(0xffffffffu, r, o);
-            q += __shfl_xor_sync(0xffffffffu, q, o);
-        }
-        if (threadIdx.x == 0) mean_s = make_double2(r / ((double)n * n), q / ((double)n * n));
-    }
+    sre[threadIdx.x] = r;
+    sim[threadIdx.x] = q;
     __syncthreads();
+    for (int o = kMeanThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sre[threadIdx.x] += sre[threadIdx.x + o];
+            sim[threadIdx.x] += sim[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mean[b] = make_double2(sre[0] / ((double)n * n), sim[0] / ((double)n * n));
+}
+
+// subtract the mean and write the outputs
+template <typename T>
+__global__ void __launch_bounds__(kAddThreads) k_fftscreen_center(const cplx<T>* __restrict__ ws, const double2* __restrict__ mean,
+                                                                   int n, cplx<T>* __restrict__ out_c, T* __restrict__ out_re) {
+    const int b = blockIdx.z;
+    const double2 m = mean[b];
     const int j = blockIdx.x * kAddThreads + threadIdx.x;
     if (j >= n) return;
     const size_t at = (size_t)b * n * n + (size_t)blockIdx.y * n + j;
     const cplx<T> v = ws[at];
-    const T re = (T)((double)v.x - mean_s.x), im = (T)((double)v.y - mean_s.y);
+    const T re = (T)((double)v.x - m.x), im = (T)((double)v.y - m.y);
     if (out_c) out_c[at] = mkc<T>(re, im);
     if (out_re) out_re[at] = re;
 }
@@ -142,14 +152,13 @@ template <typename T> int gather_t(const FftScreenLaunch& a, cudaStream_t st) {
 
 template <typename T> int finish_t(const FftScreenLaunch& a, cudaStream_t st) {
     const int per_row = (a.n + kAddThreads - 1) / kAddThreads;
-    if (a.nterms > 0) {
-        const dim3 tg((a.n + 127) / 128, a.nterms, a.nscreens);
-        k_fftscreen_tables<<<tg, 128, 0, st>>>(a.terms, a.nterms, a.x, a.y, a.n, a.ex, a.ey);
+    if (a.ngroups > 0) {
+        const dim3 tg((a.n + 127) / 128, a.ngroups, a.nscreens);
+        k_fftscreen_tables<<<tg, 128, 0, st>>>(a.terms, a.goff, a.nterms, a.ngroups, a.x, a.y, a.n, a.ex, a.ey);
     }
     const dim3 grid(per_row, a.n, a.nscreens);
-    k_fftscreen_add<T><<<grid, kAddThreads, 0, st>>>((cplx<T>*)a.ws, a.ex, a.ey, a.nterms, a.n, a.partials);
-    const dim3 rg((a.n + 127) / 128, a.nscreens);
-    k_fftscreen_rowsum<<<rg, 128, 0, st>>>(a.partials, per_row, a.n, a.rowsum);
+    k_fftscreen_add<T><<<grid, kAddThreads, 0, st>>>((cplx<T>*)a.ws, a.ex, a.ey, a.ngroups, a.n, a.partials);
+    k_fftscreen_mean<<<a.nscreens, kMeanThreads, 0, st>>>(a.partials, per_row, a.n, a.rowsum);
     k_fftscreen_center<T><<<grid, kAddThreads, 0, st>>>((const cplx<T>*)a.ws, a.rowsum, a.n, (cplx<T>*)a.out_complex, (T*)a.out_real);
     return (int)cudaGetLastError();
 }
@@ -162,6 +171,6 @@ int launch_fftscreen_gather(int prec, const FftScreenLaunch& a, cudaStream_t st)
 int launch_fftscreen_finish(int prec, const FftScreenLaunch& a, cudaStream_t st) {
     return prec == 0 ? finish_t<float>(a, st) : finish_t<double>(a, st);
 }
-int fftscreen_finish_launches(const FftScreenLaunch& a) { return a.nterms > 0 ? 4 : 3; }
+int fftscreen_finish_launches(const FftScreenLaunch& a) { return a.ngroups > 0 ? 4 : 3; }
 
 }  // namespace pa

@@ -20,7 +20,14 @@ def main():
     ctx = eng.grid_context(pa.RectGrid(n, 1.5e-3))
     spec = torch.randn((batch, n, n), dtype=torch.complex64, device="cuda")
     out = torch.empty((batch, n, n), dtype=torch.float32, device="cuda")
-    terms = np.ascontiguousarray(np.random.default_rng(0).standard_normal((batch, nterms, 4)))
+    # the reference's pattern: 3 x 3 patches (centre dropped) at spacing df / 3^(level+1) -> 3 distinct fx per level
+    rng = np.random.default_rng(0)
+    df = 1 / (n * 1.5e-3)
+    rows = []
+    for level in range((nterms + 7) // 8):
+        d = df / 3 ** (level + 1)
+        rows += [(a * d, b * d, *rng.standard_normal(2)) for a in (-1, 0, 1) for b in (-1, 0, 1) if (a, b) != (0, 0)]
+    terms = np.ascontiguousarray(np.tile(np.array(rows[:nterms], dtype=np.float64), (batch, 1, 1)))
     stream = nat.stream_ptr()
 
     def call():
