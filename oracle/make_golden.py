@@ -195,6 +195,31 @@ def case_su(pa, p, seed):
                         measures=measures_of(pa, ch, out), versions=_versions(), **params_arrays(p))
 
 
+def case_wind_su(pa, p, seed, speed, calls):
+    """WindSUPhaseScreen channel (phase_screens.py:182-215): `calls` successive Channel.run outputs of one channel
+    (the screens translate by `speed` per call) and the screens of the first call."""
+    ch = pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]),
+        source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.WindSUPhaseScreen(
+                pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"]), speed,
+                model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])),
+            length=p["length"], count=p["count"]),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
+    np.random.seed(seed)
+    screens0 = []
+    fields = []
+    for u, phi in ch.generator(pupil=False, store_output=True):
+        screens0.append(np.asarray(phi))
+    fields.append(np.asarray(ch.output))
+    for _ in range(calls - 1):
+        fields.append(np.asarray(ch.run(pupil=False)))
+    cn0 = np.asarray(ch.path.phase_screens[0].cnp)
+    np.savez_compressed(os.path.join(OUT, "windsu128.npz"), seed=seed, speed=speed, screens0=np.stack(screens0),
+                        fields=np.stack(fields), cnp0=cn0, versions=_versions(), **params_arrays(p))
+
+
 def case_fft(pa, p, seed):
     """FFTPhaseScreen channel (phase_screens.py:37-67) with subharmonic levels.  The coefficient arrays handed to
     ifft2 are captured by wrapping the name the reference module calls (the reference code itself is untouched)."""
@@ -245,6 +270,7 @@ def main():
     case_simulation(pa, small, seed=2024, count=6)
     case_time_series(pa, small, seed=77, count=3, times=(0.0, 0.012, 0.05))
     case_su(pa, dict(small, count=2), seed=31)
+    case_wind_su(pa, dict(small, count=2), seed=17, speed=0.011, calls=3)
     case_fft(pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
                       pupil=0.1, subharmonics=2), seed=13)
     for f in sorted(os.listdir(OUT)):
@@ -258,6 +284,7 @@ if __name__ == "__main__":
         _small = dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, m=96,
                       f_min=1 / 1e2 / 15, f_max=1 / 8e-3, length=6e3, count=2, pupil=0.1)
         case_su(_pa, _small, seed=31)
+        case_wind_su(_pa, _small, seed=17, speed=0.011, calls=3)
         case_fft(_pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
                            pupil=0.1, subharmonics=2), seed=13)
     else:

@@ -32,7 +32,7 @@ __all__ = [
     "screen_positions", "leg_lengths", "propagate", "circle_mask", "intensity", "moments", "rytov2",
     "analytic_gaussian_field", "pdt_histogram", "beam_statistics",
     "psd_phi_f", "andrews_psd_n", "su_delta_k", "draw_su_spectrum", "fft_screen_coefficients", "draw_fft_screen",
-    "fft_screen",
+    "fft_screen", "draw_wind_su_spectrum",
 ]
 
 
@@ -191,6 +191,22 @@ def draw_su_spectrum(base: np.ndarray, Cn2: float, l0: float, L0: float, wvl: fl
     theta = 2 * np.pi * np.random.random(size=(m,)).astype(np.float32)
     noise = (np.array([1, 1j]) @ np.random.normal(size=(2, m))).astype(np.complex64)
     value = noise * np.sqrt(psd_phi_f(rho, Cn2, l0, L0, 2 * np.pi / wvl, thickness, psd_n) * np.pi * su_delta_k(base))
+    return rho, theta, value
+
+
+def draw_wind_su_spectrum(base: np.ndarray, Cn2: float, l0: float, L0: float, wvl: float, thickness: float, psd_n=mvk_psd_n):
+    """Coefficients of the frozen-flow sparse-uniform screen (phase_screens.py:189-206): same draw order as
+    draw_su_spectrum, but the unit normals are rounded to float32 BEFORE they are combined with [1, i] (the
+    `.astype(complex64)` sits on the normal array), so the product with the float32 amplitudes is complex128.
+    Call k of the screen evaluates ss_screen(..., shift=(k * speed, 0)) with these coefficients (:208-211)."""
+    m = len(base)
+    rand = np.random.random(size=(1,)).astype(np.float32)
+    rho = ring_rho(base, rand)
+    theta = 2 * np.pi * np.random.random(size=(m,)).astype(np.float32)
+    unit = np.array([1, 1j]) @ np.random.normal(size=(2, m)).astype(np.complex64)
+    ring = np.array(base**2 - np.insert(base, 0, 0)[:-1] ** 2, dtype=np.float32)
+    # float32 products in the reference's order: ((psd * pi) * (2 pi)^2) * ring   (phase_screens.py:203-205)
+    value = unit * np.sqrt(psd_phi_f(rho, Cn2, l0, L0, 2 * np.pi / wvl, thickness, psd_n) * np.pi * (2 * np.pi) ** 2 * ring)
     return rho, theta, value
 
 

@@ -124,7 +124,7 @@ class PhaseScreensPath(AbstractPath):
         sums of harmonics over one shared log-polar grid (SSPhaseScreen, SUPhaseScreen)."""
         from .phase_screens import HarmonicSumScreen
         ps = self.phase_screens
-        return len(ps) > 0 and all(isinstance(p, HarmonicSumScreen) and p.f_grid is ps[0].f_grid for p in ps)
+        return len(ps) > 0 and all(isinstance(p, HarmonicSumScreen) and p.fusable and p.f_grid is ps[0].f_grid for p in ps)
 
     def lossless_output(self, input, *args, **kwargs):
         if self._fusable() and not args:
@@ -147,16 +147,13 @@ class PhaseScreensPath(AbstractPath):
         lib, h = ctx.lib, ctx.handle
         self.init_phase_screens()
         wvl = float(self.channel.source.wvl)
-        shift = kwargs.get("shift", args[0] if args else (0, 0))
-        wind = kwargs.get("wind", args[1] if len(args) > 1 else False)
         field = _as_field(ctx, input)
         legs = self.leg_lengths()
         scales = eng.path_losses(self, legs)
         for i, phase_screen in enumerate(self.phase_screens):
             nat.check(lib.pa_vacuum_leg(h, nat.ptr(field), 1, float(legs[i]), wvl, nat.stream_ptr()))
-            if hasattr(phase_screen, "_synthesize"):
-                spectrum = phase_screen._get_spectrum(use_cached_spectrum=wind)
-                turns, phi = phase_screen._synthesize(spectrum, shift, want_turns=True, want_phi=True)
+            if hasattr(phase_screen, "_screen_for_path"):
+                turns, phi = phase_screen._screen_for_path(*args, **kwargs)
             else:
                 # any other generator (FFTPhaseScreen): the real phase as the screen returns it, reduced to turns
                 phi = phase_screen.generate(*args, **kwargs).t.to(ctx.rdtype).contiguous()

@@ -1,5 +1,5 @@
 """Random phase screens.  Mirror of /root/reference/pyatmosphere/phase_screens.py:9-34 (PhaseScreen), :70-136
-(SSPhaseScreen), :154-179 (SUPhaseScreen) and :37-67 (FFTPhaseScreen).  Spectra are drawn on the host from numpy's
+(SSPhaseScreen), :154-179 (SUPhaseScreen), :182-215 (WindSUPhaseScreen) and :37-67 (FFTPhaseScreen).  Spectra are drawn on the host from numpy's
 global RNG in the reference's order; the sum of harmonics (pa_screen_ss) and the inverse transform of the FFT
 screens (pa_screen_fft) run in libpyatm_b200.so."""
 from __future__ import annotations
@@ -54,6 +54,7 @@ class HarmonicSumScreen(PhaseScreen):
     polynomial and the contraction and to scale the fp16 operands of the tensor-core method)."""
 
     device_rng = False          # pa_rng_spectrum draws c_m = n sqrt(power_m) with fixed ring powers: SSPhaseScreen only
+    fusable = True              # the fused propagator may synthesise this screen itself from (fx, fy, c) and one shift
 
     def __init__(self, f_grid, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -101,6 +102,12 @@ class HarmonicSumScreen(PhaseScreen):
                                        eng.screen_method(n),
                                        float(np.max(np.abs(coef[m_split:]))) if m_split < m else 1.0, nat.stream_ptr()))
         return turns, phi
+
+    def _screen_for_path(self, shift=(0, 0), wind=False):
+        """(turns, phi) of the next screen for the step-by-step path: the phase is reduced mod 2 pi in float64 on the
+        device BEFORE it is rounded to the field's precision (a float32 phase of ~1e3 rad has an ulp of 6e-5 rad)."""
+        spectrum = self._get_spectrum(use_cached_spectrum=wind)
+        return self._synthesize(spectrum, shift, want_turns=True, want_phi=True)
 
     def generate_phase_screen(self, shift: Tuple[float, float] = (0, 0), wind: bool = False, real_only: bool = False):
         """phase_screens.py:108-136 / :166-179.  `wind=True` reuses the spectrum cached on this object (frozen flow)
@@ -202,6 +209,63 @@ class SUPhaseScreen(HarmonicSumScreen):
         if use_cached_spectrum:
             self._cached_spectrum = spectrum
         return spectrum
+
+
+class WindSUPhaseScreen(SUPhaseScreen):
+    """Frozen-flow sparse-uniform screen (phase_screens.py:182-215): the coefficients are drawn once, every call
+    returns the same screen translated by `speed` along x (offset = call index * speed).  As in the reference the unit
+    normals are rounded to float32 before they are combined and `generate*` takes no shift / wind arguments.  The
+    coefficients enter the kernels as complex64 (the reference carries the float32 x float32 products in double)."""
+
+    fusable = False             # carries its own translation state: served by the step-by-step path
+
+    def __init__(self, f_grid, speed, *args, **kwargs):
+        self.speed = speed
+        self.cnp = None
+        super().__init__(f_grid, *args, **kwargs)
+
+    def generate_cn(self):
+        self.rho = self.f_grid.get_rho()
+        self.theta = self.f_grid.get_theta()
+        unit = np.random.normal(size=(2, self.f_grid.points)).astype(np.complex64)
+        self.cnp = np.array([1, 1j]) @ unit
+        self.iteration = 0
+
+    def _get_spectrum(self, use_cached_spectrum=True):
+        if self.cnp is None:
+            self.generate_cn()
+        outer = self.f_grid.base
+        ring = np.array(outer**2 - np.insert(outer, 0, 0)[:-1] ** 2, dtype=np.float32)
+        # float32 products in the reference's order, ((psd pi) (2 pi)^2) ring, not psd (pi delta_k_base)
+        scale = np.sqrt(self.model.psd_phi_f(self.rho, 2 * np.pi / self.wvl, self.thickness) * np.pi * (2 * np.pi) ** 2 * ring)
+        return PolarDiscreteFunction(rho=self.rho, theta=self.theta, value=self.cnp * scale)
+
+    def _next_offset(self):
+        if self.cnp is None:
+            self.generate_cn()
+        offset = self.iteration * self.speed
+        self.iteration += 1
+        return (offset, 0)
+
+    def _screen_for_path(self, *args, **kwargs):
+        if args or kwargs:
+            raise TypeError("WindSUPhaseScreen.generate_phase_screen() takes no shift / wind arguments")
+        shift = self._next_offset()
+        return self._synthesize(self._get_spectrum(), shift, want_turns=True, want_phi=True)
+
+    def generate_phase_screen(self, real_only: bool = False):
+        gpu.require_gpu()
+        shift = self._next_offset()
+        spectrum = self._get_spectrum()
+        _, re = self._synthesize(spectrum, shift, want_turns=False, want_phi=True)
+        if real_only:
+            return DeviceArray(re)
+        _, im = self._synthesize(spectrum, shift, want_turns=False, want_phi=True, imag_part=True)
+        return DeviceArray(nat.torch_mod().complex(re, im))
+
+    def generator(self):
+        while True:
+            yield self.generate(complex=False)
 
 
 class FFTPhaseScreen(PhaseScreen):

@@ -212,3 +212,40 @@ def test_pa_screen_fft_random_spectrum_all_sizes(n, dtype):
     assert rel_l2(a, b2[0] + 2 * b2[1]) < (3e-6 if dtype == "complex64" else 1e-12)
     with pytest.raises(nat.NativeError):
         nat.check(ctx.lib.pa_screen_fft(ctx.handle, nat.ptr(spec), 2, None, 0, None, None, nat.stream_ptr()))
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_wind_su_series_vs_reference_and_oracle(dtype):
+    """Three successive runs of a WindSUPhaseScreen channel (frozen flow, speed per call) against the reference's
+    outputs (5e-3: its complex64 harmonic factors) and against the float64 oracle fed the coefficients as the kernels
+    receive them (complex64): 1e-5 / 1e-10."""
+    pa = _pa(dtype)
+    g = load_golden("windsu128")
+    p = g["params"]
+    speed = float(g["speed"])
+    ch = pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.WindSUPhaseScreen(pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"]), speed,
+                                              model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])),
+            length=p["length"], count=p["count"]),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
+    np.random.seed(int(g["seed"]))
+    outs = [ch.run(pupil=False).get() for _ in range(g["fields"].shape[0])]
+    x, y = orc.rect_xy(p["n"], p["delta"])
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    np.random.seed(int(g["seed"]))
+    spectra = [orc.draw_wind_su_spectrum(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"]) for _ in range(p["count"])]
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="f64")
+    pos = orc.screen_positions(p["length"], p["count"])
+    for k, out in enumerate(outs):
+        screens = []
+        for rho, theta, value in spectra:
+            fx, fy = orc.spectrum_to_fxy(rho, theta)
+            screens.append(orc.ss_screen(x, y, fx, fy, value.astype(np.complex64), shift=(k * speed, 0), mode="f64"))
+        want = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="f64")
+        assert rel_l2(out, want) < (1e-5 if dtype == "complex64" else 1e-10)
+        assert rel_l2(out, g["fields"][k]) < 5e-3
+    assert rel_l2(outs[1], outs[0]) > 1e-3                 # the screens did move
+    scr = next(ch.path.phase_screens[0].generator())
+    assert scr.shape == (p["n"], p["n"])

@@ -276,3 +276,25 @@ def test_andrews_model_matches_oracle():
     kappa = np.geomspace(1e-3, 5e3, 64)
     assert np.array_equal(m.psd_n(kappa), orc.andrews_psd_n(kappa, 3e-15, 4e-3, 50.0))
     assert np.array_equal(m.psd_phi_f(kappa, 7.7e6, 300.0), orc.psd_phi_f(kappa, 3e-15, 4e-3, 50.0, 7.7e6, 300.0, orc.andrews_psd_n))
+
+
+def test_wind_su_screen_state_and_routing():
+    g = load_golden("windsu128")
+    p = g["params"]
+    screen = pa.WindSUPhaseScreen(pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"]), float(g["speed"]),
+                                  model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]))
+    ch = _n4_channel(screen)
+    ch.path.init_phase_screens()
+    assert not ch.path._fusable()                    # carries its own translation state -> step-by-step path
+    first = ch.path.phase_screens[0]
+    np.random.seed(int(g["seed"]))
+    sp = first._get_spectrum()
+    assert np.array_equal(first.cnp, g["cnp0"]) and sp.value.dtype == np.complex128
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    np.random.seed(int(g["seed"]))
+    rho, theta, value = orc.draw_wind_su_spectrum(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"])
+    assert np.array_equal(sp.rho, rho) and np.array_equal(sp.theta, theta) and np.array_equal(sp.value, value)
+    assert [first._next_offset() for _ in range(3)] == [(0.0, 0), (float(g["speed"]), 0), (2 * float(g["speed"]), 0)]
+    assert first._get_spectrum() is not sp and np.array_equal(first._get_spectrum().value, value)     # drawn once
+    with pytest.raises(TypeError):
+        first._screen_for_path(shift=(0, 0.1))

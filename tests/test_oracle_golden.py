@@ -307,3 +307,29 @@ def test_fft_screen_matches_direct_sum():
     assert rel_l2(got, direct - direct.mean()) < 1e-13
     a = orc.fft_screen(2 * cn, [], x, y, mode="f64")
     assert rel_l2(a, 2 * got) < 1e-14
+
+
+def test_wind_su_series_equals_reference():
+    """WindSUPhaseScreen (phase_screens.py:182-215): coefficients drawn once per screen object at its first call (float32-
+    rounded unit normals), call k translated by k * speed along x; three successive Channel.run outputs of the reference."""
+    g = load_golden("windsu128")
+    p = g["params"]
+    x, y = _axes(p)
+    base = orc.logpolar_base(p["m"], p["f_min"], p["f_max"])
+    speed = float(g["speed"])
+    np.random.seed(int(g["seed"]))
+    spectra = [orc.draw_wind_su_spectrum(base, p["Cn2"], p["l0"], p["L0"], p["wvl"], p["length"] / p["count"]) for _ in range(p["count"])]
+    assert spectra[0][2].dtype == np.complex128
+    pos = orc.screen_positions(p["length"], p["count"])
+    u0 = orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="ref")
+    for k in range(g["fields"].shape[0]):
+        screens = []
+        for rho, theta, value in spectra:
+            fx, fy = orc.spectrum_to_fxy(rho, theta)
+            screens.append(orc.ss_screen(x, y, fx, fy, value, shift=(k * speed, 0), mode="ref", diag_product=True))
+        if k == 0:
+            for s, phi in enumerate(screens):
+                assert np.max(np.abs(phi - g["screens0"][s])) <= 2e-6 * np.max(np.abs(phi)) + 1e-6
+        # call 0 is what Channel.generator stores (no trailing loss step; losses are 0 here), calls 1.. are Channel.run
+        out = orc.propagate(u0, screens, p["length"], pos, p["wvl"], p["delta"], mode="ref")
+        assert rel_l2(out, g["fields"][k]) < 2e-6
