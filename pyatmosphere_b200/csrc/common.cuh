@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace pa {
@@ -83,6 +84,22 @@ template <typename C> __device__ __forceinline__ C cmul_mi(C a) { C r; r.x = a.y
 // a * (+i)
 template <typename C> __device__ __forceinline__ C cmul_pi(C a) { C r; r.x = -a.y; r.y = a.x; return r; }
 template <typename C> __device__ __forceinline__ C cswap(C a) { C r; r.x = a.y; r.y = a.x; return r; }
+
+// cudaFuncSetAttribute is a per-device setting: remember on which devices a kernel's dynamic shared-memory limit has
+// been raised (one process may hold contexts on several GPUs even though the intended model is one process per GPU).
+struct SmemOptIn {
+    std::atomic<unsigned long long> devices{0};
+    template <typename K> cudaError_t raise(K kern, int bytes) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        const unsigned long long bit = 1ull << (dev & 63);
+        if (devices.load(std::memory_order_relaxed) & bit) return cudaSuccess;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) devices.fetch_or(bit, std::memory_order_relaxed);
+        return e;
+    }
+};
 
 __host__ __device__ constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
 

@@ -621,12 +621,8 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
         if (phase == 0) return (int)cudaGetLastError();
     }
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_screen_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_done = true;
-    }
+    static SmemOptIn attr_done;
+    if (cudaError_t e = attr_done.raise(k_screen_tc, SMEM_BYTES); e != cudaSuccess) return (int)e;
     TcArgs g;
     g.a = a;
     g.P = P;
