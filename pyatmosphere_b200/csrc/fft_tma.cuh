@@ -21,6 +21,11 @@
 namespace pa {
 
 constexpr int kSlots = 3;
+// Column pass: three slots, or two (the refill of the idle slot is then issued in the middle of the next tile, when the
+// store of the previous one has long left shared memory).  Two slots leave ~96 KiB of L1 for the twiddle / transfer-
+// function tables; measured per size (tools/prof_sizes.py, us per pass, 3 vs 2 slots): 1024: 46.5 / 50.4, 2048: 202.7 /
+// 202.1, 4096: 283.7 / 260.9, 8192 (split pass): 633 / 656 -> two slots at 4096 only.
+template <int N> struct ColSlots { static constexpr int value = N == 4096 ? 2 : 3; };
 #ifndef PA_TMA_ROW_THREADS
 #define PA_TMA_ROW_THREADS 128      // row pass: small CTAs (one 2048-point row each), several per SM
 #endif
@@ -47,7 +52,8 @@ template <typename T, int N, int E> struct TmaGeo {
     static constexpr int THREADS = TC * TPF;
     static constexpr int SLOT = TC * N * (int)sizeof(C);
     static constexpr int BOXR = N < 256 ? N : 256;                          // rows per tensor box
-    static constexpr int SMEM = kSlots * SLOT + 64;
+    static constexpr int SLOTS = ColSlots<N>::value;
+    static constexpr int SMEM = SLOTS * SLOT + 64;
     static constexpr bool OK = TC >= 1 && THREADS <= 1024 && THREADS >= 64 && TC * (int)sizeof(C) >= 16 && TC <= 32 &&
                                TmaRowGeo<T, N, E>::OK;
 };
@@ -132,24 +138,24 @@ template <typename T, int N, int E>
 __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
     using C = cplx<T>;
     using G = TmaGeo<T, N, E>;
-    constexpr int TC = G::TC, BOXR = G::BOXR;
+    constexpr int TC = G::TC, BOXR = G::BOXR, kColSlots = G::SLOTS;
     constexpr int kSlotBytes = G::SLOT;
     const int TILES_PER_FIELD = a.ncols / TC;       // tiles per block of N rows
     constexpr int BOX_BYTES = BOXR * TC * (int)sizeof(C);
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     C* slots = reinterpret_cast<C*>(smem_tma);
     const uint32_t slot0 = ptx::smem_u32(smem_tma);
-    const uint32_t bar0 = slot0 + kSlots * kSlotBytes;
+    const uint32_t bar0 = slot0 + kColSlots * kSlotBytes;
     const int c = threadIdx.x % TC, t = threadIdx.x / TC;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < kColSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
         ptx::fence_mbar_init();
     }
     __syncthreads();
     auto issue_load = [&](int k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) return;
-        const int slot = k % kSlots;
+        const int slot = k % kColSlots;
         const int b = tile / TILES_PER_FIELD, col0 = (tile % TILES_PER_FIELD) * TC;
         ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
 #pragma unroll
@@ -164,10 +170,10 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
     for (int k = 0;; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) break;
-        const int slot = k % kSlots;
+        const int slot = k % kColSlots;
         C* sm = slots + (size_t)slot * (kSlotBytes / sizeof(C));
         const int col = (tile % TILES_PER_FIELD) * TC + c;
-        ptx::mbar_wait(bar0 + 8 * slot, (k / kSlots) & 1);
+        ptx::mbar_wait(bar0 + 8 * slot, (k / kColSlots) & 1);
         C v[E];
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = sm[reg_pos<N, E, 0>(t, i) * TC + c];
@@ -182,6 +188,14 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
                 v[i] = cmul(v[i], h);
             }
         }
+        if constexpr (kColSlots == 2) {
+            // two-slot ring: the other slot still holds tile k-1, whose store was committed at the end of the previous
+            // iteration and has long left shared memory by now; refill it with tile k+1 (half a tile time ahead of its use)
+            if (threadIdx.x == 0 && k >= 1) {
+                ptx::bulk_wait_read<0>();
+                issue_load(k + 1);
+            }
+        }
         fft_inv<T, N, E>(v, t, sm, addr, a.tw);
         __syncthreads();
 #pragma unroll
@@ -193,8 +207,10 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
 #pragma unroll
             for (int r = 0; r < N / BOXR; ++r) ptx::tma_store_2d(&tmap, col0 * 2, b * N + r * BOXR, slot0 + slot * kSlotBytes + r * BOX_BYTES);
             ptx::bulk_commit();
-            ptx::bulk_wait_read<1>();
-            issue_load(k + 2);
+            if constexpr (kColSlots >= 3) {
+                ptx::bulk_wait_read<1>();
+                issue_load(k + 2);
+            }
         }
     }
     if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
