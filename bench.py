@@ -314,6 +314,7 @@ def run_gpu(args):
 
     # ---- roofline of the FFT passes (algorithmic bytes: 4 N^2 8 B per launch = half a split-step stage) -----
     roof = None
+    roof_screen = None
     cpu = None
     if rank == 0:
         field = ctx.empty_field(B)
@@ -349,6 +350,49 @@ def run_gpu(args):
                 "per_kernel_us": {k: v * 1e6 for k, v in times.items()},
                 "stage_us_per_realization": sum(times.values()) * 1e6 / B,
                 "stage_frac_of_hbm_roofline": (8 * n * n * 8 * B) / sum(times.values()) / 1e9 / peak}
+        # ---- tensor-pipe roofline of the screen synthesis (pa_screen_ss, tcgen05 path): B screens per call, preparation
+        # kernels included.  Executed MMA flops = 3 split-fp16 products x 2 N^2 K2 (K2 = 2 x high rings, padded to 32);
+        # algorithmic flops = 4 N^2 M.  Peak = measured dense bf16 cuBLAS throughput (same pipe, same rate).
+        roof_screen = None
+        try:
+            ps0 = ch.path.phase_screens[0]
+            m_split, degree = ps0.low_ring_plan()
+            method = eng.screen_method(n)
+            if method == nat.PA_SCREEN_TC:
+                fx_d = torch.empty((B, M), dtype=torch.float32, device=dev)
+                fy_d = torch.empty_like(fx_d)
+                cf_d = torch.empty((B, M, 2), dtype=torch.float32, device=dev)
+                nat.check(lib.pa_rng_spectrum(h, 99, 0, B, 0, 1, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d),
+                                              nat.ptr(cf_d), stream))
+                bound = eng.coef_bound(ps0._ring_power(), m_split)
+
+                def screens():
+                    nat.check(lib.pa_screen_ss(h, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), M, m_split, degree, 0.0, 0.0, B,
+                                               nat.ptr(turns), None, 0, method, bound, stream))
+                for _ in range(3):
+                    screens()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                a.record()
+                for _ in range(reps):
+                    screens()
+                b.record()
+                torch.cuda.synchronize()
+                t_scr = a.elapsed_time(b) / reps * 1e-3
+                k2 = -(-2 * (M - m_split) // 32) * 32
+                mma_flops = 3 * 2.0 * n * n * k2 * B
+                try:
+                    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                        tpeak, tsrc = float(json.load(f)["bf16_tflops"]), "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)"
+                except Exception:
+                    tpeak, tsrc = 2250.0, "nominal dense bf16 (no MEASURED_PEAKS.json)"
+                roof_screen = {"bound": "tensor", "kernel": "pa_screen_ss (k_factors_tc + polynomial nodes + k_screen_tc)",
+                               "achieved": mma_flops / t_scr / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": mma_flops / t_scr / 1e12 / tpeak,
+                               "peak_source": tsrc, "us_per_screen": t_scr * 1e6 / B, "executed_mma_flops_per_screen": mma_flops / B,
+                               "algorithmic_flops_per_screen": 4.0 * n * n * M, "rings_in_contraction": int(M - m_split),
+                               "rings_as_polynomial": int(m_split)}
+        except Exception as e:          # noqa: BLE001  (an extra, never fatal for the bench line)
+            roof_screen = {"error": repr(e)}
         # ---- CPU baseline: numpy port of the reference, one realization on one core ------------------------
         if not args.no_cpu:
             _cpu_init(cpu_psd())
@@ -373,7 +417,7 @@ def run_gpu(args):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "pa_simulate_batch (C ABI, host buffers in, per-realization table out)"},
-            "roofline": roof, "cpu_baseline": cpu,
+            "roofline": roof, "roofline_screen": roof_screen, "cpu_baseline": cpu,
             "stats_check": {"hist_total": int(hist.sum().item()), "mean_eta": float(tab[:, nat.MEASURE_HEAD].mean().item())},
         }
         print(json.dumps(line))
