@@ -24,6 +24,7 @@
 // (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
 #include <cuda_fp16.h>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "internal_screen.h"
@@ -69,6 +70,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     atomicExch(err, 1);     // never spin for ever on the GPU box: flag and abort the kernel
     __trap();
 }
+// pure polling variant (mbarrier.test_wait never suspends the thread): for barriers completed from the other SM of a pair
+__device__ __forceinline__ void mbar_poll(uint32_t bar, uint32_t parity, int* err) {
+    uint32_t ok = 0;
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (ok) return;
+    }
+    atomicExch(err, 1);
+    __trap();
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(bytes), "r"(bar)
@@ -90,6 +106,35 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// ---- CTA-pair (cta_group::2) helpers: one tcgen05.mma drives the tensor cores of both SMs of a 2-CTA cluster --------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the mbarrier at the same shared-memory offset in CTA `rank` of this cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
+    asm volatile(
+        "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// completion of all earlier MMAs of the pair -> one arrival on the mbarrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
@@ -125,6 +170,16 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 // instruction descriptor: fp32 accumulate, fp16 A and B, both K-major, M = 128, N = 256
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// CTA pair: M = 256 (128 rows per CTA), N = 256 (each CTA stages 128 of the columns)
+constexpr uint32_t IDESC_PAIR = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
+// shared-memory ring: single CTA 3 stages of P (16 KiB) + Q (32 KiB); pair 6 stages of P (16 KiB) + half of Q (16 KiB)
+template <bool PAIR> struct Ring {
+    static constexpr int Q_BYTES = PAIR ? Q_STAGE / 2 : Q_STAGE;
+    static constexpr int Q_HALF_BYTES = Q_BYTES / 2;               // hi or lo block
+    static constexpr int BYTES = P_STAGE + Q_BYTES;
+    static constexpr int N = PAIR ? 6 : STAGES;
+    static constexpr int NBARS = 2 * N + 6 + (PAIR ? N : 0);
+};
 
 // ---- operand generation -----------------------------------------------------------------------------------
 // Global layout (fp16): P: [screen][row block i/128][k block k/32]{hi,lo}[k chunk (k%32)/8][row group (i%128)/8][i%8][k%8]
@@ -142,7 +197,7 @@ __device__ __forceinline__ Split split16(float v) {
     return s;
 }
 
-__global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, __half* Q, int kpad) {
+__global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, __half* Q, int kpad, int pair) {
     const int idx = blockIdx.x * 128 + threadIdx.x;           // row i (P) or column j (Q)
     const int chunk = blockIdx.y;                              // k chunk of 8
     const bool is_q = (blockIdx.z & 1) != 0;
@@ -188,8 +243,14 @@ __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, _
     const int blk = idx / tile, within = idx % tile;
     const int kb = chunk / 4, kc = chunk % 4;
     __half* base = is_q ? Q : P;
-    char* dst = (char*)base + (((size_t)s * nblk + blk) * (kpad / BK) + kb) * (size_t)(2 * half_bytes) +
-                (size_t)kc * (tile / 8) * 128 + (size_t)(within / 8) * 128 + (within % 8) * 16;
+    // within one hi / lo block: [k chunk][col or row group][8][8]; for CTA pairs the Q block is stored as two contiguous
+    // halves of 128 columns (one per CTA of the pair), each [k chunk][16 col groups][8][8]
+    size_t inner = (size_t)kc * (tile / 8) * 128 + (size_t)(within / 8) * 128 + (within % 8) * 16;
+    if (is_q && pair) {
+        const int cg = within / 8;
+        inner = (size_t)(cg / 16) * (half_bytes / 2) + (size_t)kc * 16 * 128 + (size_t)(cg % 16) * 128 + (within % 8) * 16;
+    }
+    char* dst = (char*)base + (((size_t)s * nblk + blk) * (kpad / BK) + kb) * (size_t)(2 * half_bytes) + inner;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(dst + half_bytes) = *reinterpret_cast<const uint4*>(lo);
 }
@@ -320,16 +381,27 @@ struct TcArgs {
 };
 #define PA_TRACE(slot) do { if (g.trace && blockIdx.x == 0 && it < 16) g.trace[it * 16 + (slot)] = clock64(); } while (0)
 
+// PAIR = true (experimental, PYATM_TC_PAIR=1): launched as clusters of two CTAs that share one 256 x 256 output tile
+// (cta_group::2).  Each CTA stages its own 128 rows of P and 128 of the 256 columns of Q, so an MMA reads 8 KiB of shared
+// memory per SM instead of 12 KiB and a K block fills 32 KiB instead of 48 KiB: the single-CTA kernel is bound by shared-
+// memory bandwidth (operand reads + TMA fills = 150 B/clk against 128 B/clk per SM; measured per 8 screens: MMA floor 75 us,
+// bulk copies alone 67 us, both together 105 us).  The leader CTA (cluster rank 0) issues the MMAs for both; the peer's
+// MMA warp only relays "my operands have landed".
+template <bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const ScreenLaunch& a = g.a;
+    using R = Ring<PAIR>;
+    constexpr int STAGES = R::N, STAGE_BYTES = R::BYTES;
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
     unsigned char* stage_base = smem;                                        // STAGES * STAGE_BYTES
     float* sN = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);       // [TILE_NODES]{hi, lo, turns}[128]: nodes of this tile
     float* sX = sN + TILE_NODES * NODE_FLOATS;                               // [2][256] column jitter, per tile parity
     const int D = a.degree;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sX + 2 * TN);
-    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] nodes_full, [2S+5] nodes_free
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+    // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty, [2S+4] nodes_full, [2S+5] nodes_free,
+    // pair only: [2S+6..3S+6) peer_full (in the leader: the peer's operands of that stage have landed)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + R::NBARS);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -337,6 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
     auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
     auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
     const uint32_t ufull_bar = bar0 + 8u * (2 * STAGES + 4), ufree_bar = bar0 + 8u * (2 * STAGES + 5);
+    auto peerfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 6 + s); };
 
     constexpr int W_PROD = EPI_WARPS, W_MMA = EPI_WARPS + 1, W_ALLOC = EPI_WARPS + 2;   // high warp ids: the scheduler favours them
     if (warp == W_MMA && lane == 0) {
@@ -346,23 +419,35 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), EPI_WARPS);   // one arrival per epilogue warp
+            mbar_init(tempty_bar(b), EPI_WARPS * (PAIR ? 2 : 1));   // one arrival per epilogue warp (of both CTAs)
         }
         mbar_init(ufull_bar, 1);
         mbar_init(ufree_bar, EPI_WARPS);
+        if constexpr (PAIR)
+            for (int s = 0; s < STAGES; ++s) mbar_init(peerfull_bar(s), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     } else if (warp == W_ALLOC) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {      // the same warp of both CTAs allocates the same columns in both tensor memories
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();        // the peer's barriers exist before anything arrives on them remotely
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int n = a.n;
     const int rblocks = n / TM, cblocks = n / TN;
-    const int tiles_per_screen = rblocks * cblocks;
+    // work items: single CTA = one 128 x 256 tile; pair = one 256 x 256 tile, this CTA owning row block 2 * pair_row + rank
+    const int tiles_per_screen = (PAIR ? rblocks / 2 : rblocks) * cblocks;
+    const int first_tile = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto row_block = [&](int rem) { return PAIR ? 2 * (rem / cblocks) + (int)rank : rem / cblocks; };
 
     if (warp == W_PROD) {
         // ===== producer: one bulk copy per operand and stage =====
@@ -370,14 +455,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, ++it) {
                 const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
-                const int rb = rem / cblocks, cb = rem % cblocks;
+                const int rb = row_block(rem), cb = rem % cblocks;
                 PA_TRACE(0);
                 const char* psrc = (const char*)g.P + ((size_t)s * rblocks + rb) * g.kblocks * (size_t)P_STAGE;
                 const char* qsrc = (const char*)g.Q + ((size_t)s * cblocks + cb) * g.kblocks * (size_t)Q_STAGE;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1, g.err);
+                    if constexpr (PAIR) mbar_poll(empty_bar(stage), phase ^ 1, g.err);
+                    else mbar_wait(empty_bar(stage), phase ^ 1, g.err);
                     if (g.swap_lbo_sbo & 2) {
                         mbar_arrive(full_bar(stage));
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -388,8 +474,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     constexpr int CH = 8192;      // several 8 KiB copies in flight instead of two large ones
 #pragma unroll
                     for (int o = 0; o < P_STAGE; o += CH) bulk_g2s(dst + o, psrc + (size_t)kb * P_STAGE + o, CH, full_bar(stage));
+                    if constexpr (PAIR) {
 #pragma unroll
-                    for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
+                        for (int hl = 0; hl < 2; ++hl)      // this CTA's 128 columns are one contiguous 8 KiB piece of the hi / lo block
+                            bulk_g2s(dst + P_STAGE + hl * R::Q_HALF_BYTES,
+                                     qsrc + (size_t)kb * Q_STAGE + (size_t)hl * Q_HALF + rank * R::Q_HALF_BYTES, R::Q_HALF_BYTES, full_bar(stage));
+                    } else {
+#pragma unroll
+                        for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
                 PA_TRACE(1);
@@ -397,38 +490,63 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         }
     } else if (warp == W_MMA) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (PAIR && rank != 0) {
+            // ===== peer CTA: no MMAs of its own -- tell the leader when this CTA's operands of a stage have landed =====
+            if (lane == 0) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
+                    for (int kb = 0; kb < g.kblocks; ++kb) {
+                        mbar_wait(full_bar(stage), phase, g.err);
+                        mbar_arrive_remote(peerfull_bar(stage), 0);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
+            constexpr int QCOLS = PAIR ? TN / 2 : TN;          // columns of Q staged in this CTA
             const uint32_t p_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(TM / 8) * 128u, p_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(TM / 8) * 128u : 128u;
-            const uint32_t q_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(TN / 8) * 128u, q_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(TN / 8) * 128u : 128u;
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            const uint32_t q_lbo = (g.swap_lbo_sbo & 1) ? 128u : (uint32_t)(QCOLS / 8) * 128u, q_sbo = (g.swap_lbo_sbo & 1) ? (uint32_t)(QCOLS / 8) * 128u : 128u;
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, ++it) {
                 const int buf = it & 1;
                 PA_TRACE(2);
-                mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);     // epilogue has drained this accumulator
+                if constexpr (PAIR) mbar_poll(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);
+                else mbar_wait(tempty_bar(buf), ((it >> 1) & 1) ^ 1, g.err);     // epilogue has drained this accumulator
                 tc_fence_after();
                 PA_TRACE(3);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
                     mbar_wait(full_bar(stage), phase, g.err);
+                    if constexpr (PAIR) mbar_poll(peerfull_bar(stage), phase, g.err);
                     tc_fence_after();
                     const uint32_t sp = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
                     const uint32_t sq = sp + P_STAGE;
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
                         if (g.swap_lbo_sbo & 4) break;
-                        const uint32_t poff = (uint32_t)k16 * 2u * (TM / 8) * 128u, qoff = (uint32_t)k16 * 2u * (TN / 8) * 128u;
+                        const uint32_t poff = (uint32_t)k16 * 2u * (TM / 8) * 128u, qoff = (uint32_t)k16 * 2u * (QCOLS / 8) * 128u;
                         const uint64_t ah = umma_desc(sp + poff, p_lbo, p_sbo), al = umma_desc(sp + P_HALF + poff, p_lbo, p_sbo);
-                        const uint64_t bh = umma_desc(sq + qoff, q_lbo, q_sbo), bl = umma_desc(sq + Q_HALF + qoff, q_lbo, q_sbo);
-                        umma_f16(d_tmem, al, bh, IDESC, (kb | k16) != 0);
-                        umma_f16(d_tmem, ah, bl, IDESC, 1);
-                        umma_f16(d_tmem, ah, bh, IDESC, 1);
+                        const uint64_t bh = umma_desc(sq + qoff, q_lbo, q_sbo), bl = umma_desc(sq + R::Q_HALF_BYTES + qoff, q_lbo, q_sbo);
+                        if constexpr (PAIR) {
+                            umma_f16_pair(d_tmem, al, bh, IDESC_PAIR, (kb | k16) != 0);
+                            umma_f16_pair(d_tmem, ah, bl, IDESC_PAIR, 1);
+                            umma_f16_pair(d_tmem, ah, bh, IDESC_PAIR, 1);
+                        } else {
+                            umma_f16(d_tmem, al, bh, IDESC, (kb | k16) != 0);
+                            umma_f16(d_tmem, ah, bl, IDESC, 1);
+                            umma_f16(d_tmem, ah, bh, IDESC, 1);
+                        }
                     }
-                    umma_commit(empty_bar(stage));       // smem slot free once these MMAs have read it
+                    // smem slot free (in both CTAs of a pair) once these MMAs have read it
+                    if constexpr (PAIR) umma_commit_pair(empty_bar(stage));
+                    else umma_commit(empty_bar(stage));
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tfull_bar(buf));             // accumulator complete
+                if constexpr (PAIR) umma_commit_pair(tfull_bar(buf));     // accumulator complete, in both CTAs
+                else umma_commit(tfull_bar(buf));
                 PA_TRACE(4);
             }
         }
@@ -439,9 +557,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             int it = 0;
             constexpr uint32_t BYTES = TILE_NODES * NODE_FLOATS * 4u, PIECE = BYTES / 3u;
             static_assert(BYTES % 48 == 0, "three 16-byte aligned pieces");
-            for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, ++it) {
                 const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
-                const int rb = rem / cblocks, cb = rem % cblocks;
+                const int rb = row_block(rem), cb = rem % cblocks;
                 if (it > 0) mbar_wait(ufree_bar, (it - 1) & 1, g.err);
                 const char* src = reinterpret_cast<const char*>(g.nodes + (((size_t)s * rblocks + rb) * g.nq + (size_t)cb * (TN / NODE_SP)) * NODE_FLOATS);
                 mbar_expect_tx(ufull_bar, BYTES);
@@ -462,9 +580,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         const int row_in_tile = ew * 32 + lane;
         const float out_scale_f = g.out_scale;
         int it = 0;
-        for (int tile = blockIdx.x; tile < g.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = first_tile; tile < g.total_tiles; tile += tile_step, ++it) {
             const int s = tile / tiles_per_screen, rem = tile % tiles_per_screen;
-            const int rb = rem / cblocks, cb = rem % cblocks;
+            const int rb = row_block(rem), cb = rem % cblocks;
             const int i = rb * TM + row_in_tile;
             float* sXt = sX + (it & 1) * TN;           // the other parity may still be read by a slower warp
             if (et < TN) sXt[et] = __ldg(g.jit + cb * TN + et);
@@ -557,18 +675,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(buf));
+            if (lane == 0) {        // the leader's MMA warp waits for the epilogue warps of both CTAs
+                if (PAIR && rank != 0) mbar_arrive_remote(tempty_bar(buf), 0);
+                else mbar_arrive(tempty_bar(buf));
+            }
             if (threadIdx.x == 0) PA_TRACE(7);
         }
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();       // neither CTA leaves (or frees tensor memory) while its peer may still touch it
     if (warp == W_ALLOC) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (TILE_NODES * NODE_FLOATS + 2 * TN) * (int)sizeof(float) + (2 * STAGES + 6) * 8 + 16;
+template <bool PAIR> constexpr int smem_bytes() {
+    return Ring<PAIR>::N * Ring<PAIR>::BYTES + (TILE_NODES * NODE_FLOATS + 2 * TN) * (int)sizeof(float) + Ring<PAIR>::NBARS * 8 + 16;
+}
+constexpr int SMEM_BYTES = smem_bytes<false>();
+constexpr int SMEM_BYTES_PAIR = smem_bytes<true>();
 
 }  // namespace tc
 
@@ -608,9 +735,15 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     __half* Q = Qall + (size_t)first_screen * pq_stride;
     // row coefficients are packed with the actual degree: [(D+1)][n] per screen inside the reserved slab
     double* U = Uall + (size_t)first_screen * u_stride;
+    // PYATM_TC_PAIR=1 selects the CTA-pair (cta_group::2) kernel and its operand layout.  It is correct (same tests) but not
+    // yet faster: 165 us against 120 us per 8 screens -- its operand pipeline alone (no MMAs, no epilogue) takes 155 us
+    // against 67 us, because every stage crosses the cluster twice (peer -> leader "operands landed" relay, leader -> both
+    // "stage free" multicast commit).  The fix is to let the peer's TMA signal the leader's barrier directly
+    // (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.  See DESIGN.md s8.
+    static const bool pair = getenv("PYATM_TC_PAIR") && atoi(getenv("PYATM_TC_PAIR")) != 0 && !(swap & 128);
     if (phase == 0 || phase == 2) {
         dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
-        k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad);
+        k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad, pair ? 1 : 0);
         if (a.degree >= 0) {
             dim3 gu((nq + 127) / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride, nq);
@@ -621,8 +754,10 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
         if (phase == 0) return (int)cudaGetLastError();
     }
-    static SmemOptIn attr_done;
-    if (cudaError_t e = attr_done.raise(k_screen_tc, SMEM_BYTES); e != cudaSuccess) return (int)e;
+    static SmemOptIn attr_done, attr_done_pair;
+    if (cudaError_t e = attr_done.raise(k_screen_tc<false>, SMEM_BYTES); e != cudaSuccess) return (int)e;
+    if (pair)
+        if (cudaError_t e = attr_done_pair.raise(k_screen_tc<true>, SMEM_BYTES_PAIR); e != cudaSuccess) return (int)e;
     TcArgs g;
     g.a = a;
     g.P = P;
@@ -637,13 +772,30 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     g.inv_h = (float)(1.0 / ((double)NODE_SP * a.dxu * a.inv_x0));
     g.out_scale = (float)(1.0 / (a.p_scale * (double)Q_SCALE));
     g.trace = nullptr;
+    if (pair) {
+        g.total_tiles = a.nscreens * (a.n / (2 * TM)) * (a.n / TN);      // 256 x 256 tiles, one per CTA pair
+        const int pairs = g.total_tiles < num_sms / 2 ? g.total_tiles : num_sms / 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES_PAIR;
+        cfg.stream = st;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2;
+        at.val.clusterDim.y = 1;
+        at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        return (int)cudaLaunchKernelEx(&cfg, k_screen_tc<true>, g);
+    }
     const int grid = g.total_tiles < num_sms ? g.total_tiles : num_sms;
     if (swap & 128) {           // debug: clock64 stamps of CTA 0 printed to stderr (synchronises)
         static long long* trace_dev = nullptr;
         if (!trace_dev) cudaMalloc(&trace_dev, 16 * 16 * sizeof(long long));
         cudaMemsetAsync(trace_dev, 0, 16 * 16 * sizeof(long long), st);
         g.trace = trace_dev;
-        k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+        k_screen_tc<false><<<grid, THREADS, SMEM_BYTES, st>>>(g);
         long long h[16 * 16];
         cudaStreamSynchronize(st);
         cudaMemcpy(h, trace_dev, sizeof(h), cudaMemcpyDeviceToHost);
@@ -656,7 +808,7 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         }
         return (int)cudaGetLastError();
     }
-    k_screen_tc<<<grid, THREADS, SMEM_BYTES, st>>>(g);
+    k_screen_tc<false><<<grid, THREADS, SMEM_BYTES, st>>>(g);
     return (int)cudaGetLastError();
 }
 
