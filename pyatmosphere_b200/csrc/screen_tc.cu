@@ -118,7 +118,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // arrive on the mbarrier at the same shared-memory offset in CTA `rank` of this cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank) {
     asm volatile(
-        "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
+        "{\n .reg .b32 ra;\n mapa.shared::cluster.u32 ra, %0, %1;\n mbarrier.arrive.shared::cluster.b64 _, [ra];\n}" ::"r"(bar),
         "r"(rank)
         : "memory");
 }
@@ -497,8 +497,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 uint32_t phase = 0;
                 for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
                     for (int kb = 0; kb < g.kblocks; ++kb) {
-                        mbar_wait(full_bar(stage), phase, g.err);
-                        mbar_arrive_remote(peerfull_bar(stage), 0);
+                        mbar_poll(full_bar(stage), phase, g.err);
+                        if (!(g.swap_lbo_sbo & 16)) mbar_arrive_remote(peerfull_bar(stage), 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -520,7 +520,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
                 for (int kb = 0; kb < g.kblocks; ++kb) {
                     mbar_wait(full_bar(stage), phase, g.err);
-                    if constexpr (PAIR) mbar_poll(peerfull_bar(stage), phase, g.err);
+                    if constexpr (PAIR)
+                        if (!(g.swap_lbo_sbo & 16)) mbar_poll(peerfull_bar(stage), phase, g.err);      // bit 16: timing experiment without the relay
                     tc_fence_after();
                     const uint32_t sp = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
                     const uint32_t sq = sp + P_STAGE;
@@ -736,10 +737,10 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     // row coefficients are packed with the actual degree: [(D+1)][n] per screen inside the reserved slab
     double* U = Uall + (size_t)first_screen * u_stride;
     // PYATM_TC_PAIR=1 selects the CTA-pair (cta_group::2) kernel and its operand layout.  It is correct (same tests) but not
-    // yet faster: 165 us against 120 us per 8 screens -- its operand pipeline alone (no MMAs, no epilogue) takes 155 us
-    // against 67 us, because every stage crosses the cluster twice (peer -> leader "operands landed" relay, leader -> both
-    // "stage free" multicast commit).  The fix is to let the peer's TMA signal the leader's barrier directly
-    // (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.  See DESIGN.md s8.
+    // yet faster: 127 us against 120 us per 8 screens.  Without the peer -> leader "operands landed" relay (debug bit 16,
+    // wrong results) it runs in 100 us, so the relay hop is what is left: the fix is to let the peer's TMA signal the leader's
+    // barrier directly (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.
+    // (A release.cluster fence on the remote arrives cost another 38 us: 165 us.)
     static const bool pair = getenv("PYATM_TC_PAIR") && atoi(getenv("PYATM_TC_PAIR")) != 0 && !(swap & 128);
     if (phase == 0 || phase == 2) {
         dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
