@@ -2,7 +2,7 @@
 
     python tools/launch_breakdown.py gpurun_out/launches.csv
 
-A step starts at the device-RNG kernel (k_rng_spectrum); the last complete step of the file is reported."""
+A step starts at the device-RNG kernel (k_rng_spectrum); the last step of the usual length is reported."""
 import csv
 import sys
 from collections import OrderedDict
@@ -18,7 +18,13 @@ def main(path):
     starts = [i for i, (k, _) in enumerate(rows) if "k_rng_spectrum" in k]
     if len(starts) < 2:
         raise SystemExit("fewer than two steps in the launch list")
-    step = rows[starts[-2]:starts[-1]]
+    # steps of the device-RNG throughput loop all have the same number of launches; later launches (host-buffer leg, roofline
+    # legs) follow the last device-RNG kernel and are not delimited by it
+    spans = [(starts[k], starts[k + 1]) for k in range(len(starts) - 1)]
+    lengths = [b - a for a, b in spans]
+    usual = max(set(lengths), key=lengths.count)
+    a0, b0 = [sp for sp, ln in zip(spans, lengths) if ln == usual][-1]
+    step = rows[a0:b0]
     step = [(k, t) for k, t in step if "pa::" in k or "tc::" in k]
     total = sum(t for _, t in step)
     agg = OrderedDict()
