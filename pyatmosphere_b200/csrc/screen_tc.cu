@@ -172,12 +172,14 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 // CTA pair: M = 256 (128 rows per CTA), N = 256 (each CTA stages 128 of the columns)
 constexpr uint32_t IDESC_PAIR = (1u << 4) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
-// shared-memory ring: single CTA 3 stages of P (16 KiB) + Q (32 KiB); pair 6 stages of P (16 KiB) + half of Q (16 KiB)
+// shared-memory ring: single CTA 3 stages of P (16 KiB) + Q (32 KiB); pair 3 stages of 2 x [P (16 KiB) + half of Q (16 KiB)]
 template <bool PAIR> struct Ring {
     static constexpr int Q_BYTES = PAIR ? Q_STAGE / 2 : Q_STAGE;
     static constexpr int Q_HALF_BYTES = Q_BYTES / 2;               // hi or lo block
-    static constexpr int BYTES = P_STAGE + Q_BYTES;
-    static constexpr int N = PAIR ? 6 : STAGES;
+    static constexpr int SUB = PAIR ? 2 : 1;                       // K blocks of 32 per stage: the pair halves its cross-CTA handshakes
+    static constexpr int KB_BYTES = P_STAGE + Q_BYTES;             // one K block of this CTA's operands
+    static constexpr int BYTES = SUB * KB_BYTES;
+    static constexpr int N = PAIR ? 3 : STAGES;
     static constexpr int NBARS = 2 * N + 6 + (PAIR ? N : 0);
 };
 
@@ -381,7 +383,7 @@ struct TcArgs {
 };
 #define PA_TRACE(slot) do { if (g.trace && blockIdx.x == 0 && it < 16) g.trace[it * 16 + (slot)] = clock64(); } while (0)
 
-// PAIR = true (experimental, PYATM_TC_PAIR=1): launched as clusters of two CTAs that share one 256 x 256 output tile
+// PAIR = true (default; PYATM_TC_PAIR=0 selects the single-CTA variant): clusters of two CTAs share one 256 x 256 output tile
 // (cta_group::2).  Each CTA stages its own 128 rows of P and 128 of the 256 columns of Q, so an MMA reads 8 KiB of shared
 // memory per SM instead of 12 KiB and a K block fills 32 KiB instead of 48 KiB: the single-CTA kernel is bound by shared-
 // memory bandwidth (operand reads + TMA fills = 150 B/clk against 128 B/clk per SM; measured per 8 screens: MMA floor 75 us,
@@ -461,7 +463,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 PA_TRACE(0);
                 const char* psrc = (const char*)g.P + ((size_t)s * rblocks + rb) * g.kblocks * (size_t)P_STAGE;
                 const char* qsrc = (const char*)g.Q + ((size_t)s * cblocks + cb) * g.kblocks * (size_t)Q_STAGE;
-                for (int kb = 0; kb < g.kblocks; ++kb) {
+                for (int kb0 = 0; kb0 < g.kblocks; kb0 += R::SUB) {
+                    const int nsub = g.kblocks - kb0 < R::SUB ? g.kblocks - kb0 : R::SUB;      // K blocks in this stage
                     if constexpr (PAIR) mbar_poll(empty_bar(stage), phase ^ 1, g.err);
                     else mbar_wait(empty_bar(stage), phase ^ 1, g.err);
                     if (g.swap_lbo_sbo & 2) {
@@ -469,19 +472,24 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_expect_tx(full_bar(stage), STAGE_BYTES);
-                    const uint32_t dst = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+                    mbar_expect_tx(full_bar(stage), (uint32_t)nsub * R::KB_BYTES);
                     constexpr int CH = 8192;      // several 8 KiB copies in flight instead of two large ones
 #pragma unroll
-                    for (int o = 0; o < P_STAGE; o += CH) bulk_g2s(dst + o, psrc + (size_t)kb * P_STAGE + o, CH, full_bar(stage));
-                    if constexpr (PAIR) {
+                    for (int sub = 0; sub < R::SUB; ++sub) {
+                        if (R::SUB > 1 && sub >= nsub) break;
+                        const int kb = kb0 + sub;
+                        const uint32_t dst = smem_u32(stage_base + (size_t)stage * STAGE_BYTES + (size_t)sub * R::KB_BYTES);
 #pragma unroll
-                        for (int hl = 0; hl < 2; ++hl)      // this CTA's 128 columns are one contiguous 8 KiB piece of the hi / lo block
-                            bulk_g2s(dst + P_STAGE + hl * R::Q_HALF_BYTES,
-                                     qsrc + (size_t)kb * Q_STAGE + (size_t)hl * Q_HALF + rank * R::Q_HALF_BYTES, R::Q_HALF_BYTES, full_bar(stage));
-                    } else {
+                        for (int o = 0; o < P_STAGE; o += CH) bulk_g2s(dst + o, psrc + (size_t)kb * P_STAGE + o, CH, full_bar(stage));
+                        if constexpr (PAIR) {
 #pragma unroll
-                        for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
+                            for (int hl = 0; hl < 2; ++hl)      // this CTA's 128 columns are one contiguous 8 KiB piece of the hi / lo block
+                                bulk_g2s(dst + P_STAGE + hl * R::Q_HALF_BYTES,
+                                         qsrc + (size_t)kb * Q_STAGE + (size_t)hl * Q_HALF + rank * R::Q_HALF_BYTES, R::Q_HALF_BYTES, full_bar(stage));
+                        } else {
+#pragma unroll
+                            for (int o = 0; o < Q_STAGE; o += CH) bulk_g2s(dst + P_STAGE + o, qsrc + (size_t)kb * Q_STAGE + o, CH, full_bar(stage));
+                        }
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
-                    for (int kb = 0; kb < g.kblocks; ++kb) {
+                    for (int kb0 = 0; kb0 < g.kblocks; kb0 += R::SUB) {
                         mbar_poll(full_bar(stage), phase, g.err);
                         if (!(g.swap_lbo_sbo & 16)) mbar_arrive_remote(peerfull_bar(stage), 0);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -518,12 +526,17 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                 tc_fence_after();
                 PA_TRACE(3);
                 const uint32_t d_tmem = tmem_base + (uint32_t)buf * TN;
-                for (int kb = 0; kb < g.kblocks; ++kb) {
+                for (int kb0 = 0; kb0 < g.kblocks; kb0 += R::SUB) {
+                    const int nsub = g.kblocks - kb0 < R::SUB ? g.kblocks - kb0 : R::SUB;
                     mbar_wait(full_bar(stage), phase, g.err);
                     if constexpr (PAIR)
                         if (!(g.swap_lbo_sbo & 16)) mbar_poll(peerfull_bar(stage), phase, g.err);      // bit 16: timing experiment without the relay
                     tc_fence_after();
-                    const uint32_t sp = smem_u32(stage_base + (size_t)stage * STAGE_BYTES);
+#pragma unroll
+                  for (int sub = 0; sub < R::SUB; ++sub) {
+                    if (R::SUB > 1 && sub >= nsub) break;
+                    const int kb = kb0 + sub;
+                    const uint32_t sp = smem_u32(stage_base + (size_t)stage * STAGE_BYTES + (size_t)sub * R::KB_BYTES);
                     const uint32_t sq = sp + P_STAGE;
 #pragma unroll
                     for (int k16 = 0; k16 < BK / 16; ++k16) {
@@ -541,6 +554,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                             umma_f16(d_tmem, ah, bh, IDESC, 1);
                         }
                     }
+                  }
                     // smem slot free (in both CTAs of a pair) once these MMAs have read it
                     if constexpr (PAIR) umma_commit_pair(empty_bar(stage));
                     else umma_commit(empty_bar(stage));
@@ -736,12 +750,12 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     __half* Q = Qall + (size_t)first_screen * pq_stride;
     // row coefficients are packed with the actual degree: [(D+1)][n] per screen inside the reserved slab
     double* U = Uall + (size_t)first_screen * u_stride;
-    // PYATM_TC_PAIR=1 selects the CTA-pair (cta_group::2) kernel and its operand layout.  It is correct (same tests) but not
-    // yet faster: 127 us against 120 us per 8 screens.  Without the peer -> leader "operands landed" relay (debug bit 16,
-    // wrong results) it runs in 100 us, so the relay hop is what is left: the fix is to let the peer's TMA signal the leader's
-    // barrier directly (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.
-    // (A release.cluster fence on the remote arrives cost another 38 us: 165 us.)
-    static const bool pair = getenv("PYATM_TC_PAIR") && atoi(getenv("PYATM_TC_PAIR")) != 0 && !(swap & 128);
+    // CTA pairs (cta_group::2) by default; PYATM_TC_PAIR=0 selects the single-CTA kernel and its operand layout.
+    // Per 8 screens of 2048^2: single 120 us, pair 113 us (two K blocks per stage; 127 us with one, 165 us with a
+    // release.cluster fence on the remote arrives).  Without the peer -> leader "operands landed" relay (debug bit 16, wrong
+    // results) the pair runs in 100 us: the next step is to let the peer's TMA signal the leader's barrier directly
+    // (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.
+    static const bool pair = !(getenv("PYATM_TC_PAIR") && atoi(getenv("PYATM_TC_PAIR")) == 0) && !(swap & 128);
     if (phase == 0 || phase == 2) {
         dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
         k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad, pair ? 1 : 0);

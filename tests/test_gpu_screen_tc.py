@@ -124,13 +124,14 @@ def test_full_size_tc_vs_complex128():
     assert rel_l2(fields["complex64"], fields["complex128"]) < 2e-5
 
 
-def test_cta_pair_kernel_matches_oracle_in_a_subprocess():
-    """The experimental cta_group::2 variant of the contraction (PYATM_TC_PAIR=1, read once per process) must stay
-    correct: the 256^2 oracle comparison and the full-size comparison with the exact path, in a child interpreter."""
+def test_single_cta_kernel_matches_oracle_in_a_subprocess():
+    """The contraction runs as CTA pairs (cta_group::2) by default; the single-CTA variant (PYATM_TC_PAIR=0, read once per
+    process) must stay correct too: the 256^2 oracle comparison and the full-size comparison with the exact path, in a
+    child interpreter."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, PYATM_TC_PAIR="1")
+    env = dict(os.environ, PYATM_TC_PAIR="0")
     here = os.path.dirname(os.path.abspath(__file__))
     r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", os.path.join(here, "test_gpu_screen_tc.py"),
                         "-k", "tc_screen_vs_oracle_256 or tc_matches_exact_path_full_size"],
