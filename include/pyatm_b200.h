@@ -133,7 +133,8 @@ typedef struct pa_path {
                                          1: field_dev already holds the input field in natural order */
 } pa_path;
 
-/* fx/fy/coef: [n_screens][batch][m] (one contiguous slab per path position); field_dev: [batch][N][N] result,
+/* pathes.py:61-75 (generator) drained by :53-59 (lossless_output), see pa_path above.
+ * fx/fy/coef: [n_screens][batch][m] (one contiguous slab per path position); field_dev: [batch][N][N] result,
  * natural order */
 PA_API int pa_propagate(pa_ctx* ctx, const pa_path* path, void* field_dev, int batch, const float* fx_dev,
                  const float* fy_dev, const float* coef_dev, void* stream);

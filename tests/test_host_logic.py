@@ -298,3 +298,21 @@ def test_wind_su_screen_state_and_routing():
     assert first._get_spectrum() is not sp and np.array_equal(first._get_spectrum().value, value)     # drawn once
     with pytest.raises(TypeError):
         first._screen_for_path(shift=(0, 0.1))
+
+
+def test_header_cites_the_reference_for_every_compute_entry_point():
+    """include/pyatm_b200.h: every exported function that replaces reference code carries a file:line citation of what it
+    replaces in the comment block in front of it (utility entry points -- version, error text, counters, profiling -- excepted)."""
+    hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
+    utilities = {"pa_version", "pa_last_error", "pa_device_count", "pa_launch_count", "pa_ctx_destroy", "pa_ctx_permutation",
+                 "pa_ctx_fft_geometry", "pa_fft_pass", "pa_phase_to_turns", "pa_simulate_batch_device"}
+    cite = re.compile(r"[\w/]+\.py:\d+")
+    last_comment = ""
+    checked = 0
+    for m in re.finditer(r"/\*.*?\*/|PA_API[^;(]*?\b(pa_\w+)\s*\(", hdr, flags=re.S):
+        if m.group(1) is None:
+            last_comment = m.group(0)
+        elif m.group(1) not in utilities:
+            assert cite.search(last_comment), f"{m.group(1)}: no reference citation in the preceding comment"
+            checked += 1
+    assert checked >= 13
