@@ -316,3 +316,23 @@ def test_header_cites_the_reference_for_every_compute_entry_point():
             assert cite.search(last_comment), f"{m.group(1)}: no reference citation in the preceding comment"
             checked += 1
     assert checked >= 13
+
+
+def test_c_abi_rejects_null_arguments_with_a_status_code():
+    """Every entry point that takes a context validates its arguments before touching CUDA: a null context / null pointers
+    give status PA_ERR_ARG (1) and a message through pa_last_error() -- no exception, no crash, no GPU needed."""
+    import ctypes as C
+    lib = nat.load()
+    skip = {"pa_version", "pa_last_error", "pa_launch_count", "pa_device_count", "pa_ctx_create", "pa_ctx_destroy"}
+    for name, (_, args) in nat.SIGNATURES.items():
+        if name in skip:
+            continue
+        call = [0.0 if a is C.c_double else (None if a in (C.c_void_p, C.POINTER(nat.PaPath)) else 0) for a in args]
+        assert getattr(lib, name)(*call) == 1, name
+        assert b"bad arguments" in lib.pa_last_error(), name
+    assert lib.pa_ctx_destroy(None) == 0                      # destroying nothing is not an error
+    h = C.c_void_p()
+    assert lib.pa_ctx_create(C.byref(h), 0, 100, 0) != 0      # not a power of two in [64, 8192]
+    assert b"unsupported" in lib.pa_last_error()
+    with pytest.raises(nat.NativeError):
+        nat.check(1)
