@@ -1,17 +1,25 @@
 """bench.py -- channel realizations/s of the README "advanced channel" (2048^2, 5 SS screens, 50 km) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--workload c3|c4|c5] [--impl reference]
 
-A step is one batch of B independent realizations of the whole hot path (device RNG -> 5 x [leg + screen
-synthesis + screen multiply] -> closing leg -> fused measures).  See DESIGN.md "Measurement".
+Workloads (BASELINE.json configs):
+  c3 (default, the configuration the metric is quoted on): a step is one batch of B = 160 independent realizations of the
+     whole hot path (device RNG -> 5 x [leg + screen synthesis + screen multiply] -> closing leg -> fused measures), one
+     pa_simulate_batch_device call.  `e2e` is the same batch through pa_simulate_batch with HOST coefficient buffers
+     (drawn on host threads inside the timed region), copies in and table out.
+  c4: Simulation([BeamResult, PDTResult]).run() -- the call a user of the reference makes -- for 6000 device-RNG
+     realizations of the same channel, sharded over the ranks, one all-gather of the records at the end.
+  c5: long-haul stress, 8192^2, 20 screens over 100 km, batched, complex64 (tensor-core screens) and complex128.
+See DESIGN.md "Measurement".
 """
 from __future__ import annotations
 
 import argparse
+import concurrent.futures
+import hashlib
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -23,7 +31,10 @@ sys.path.insert(0, ROOT)
 
 C3 = dict(n=2048, delta=1.5e-3, wvl=808e-9, w0=0.12, Cn2=5e-16, l0=6e-3, L0=1e3, m=2**10, f_min=1 / 1e3 / 15,
           f_max=1 / 6e-3 * 2, length=50e3, count=5, pupil=0.2)
+# config 5: twice the README extent for the twice longer path (6.1 m aperture plane), same spectrum
+C5 = dict(C3, n=8192, delta=1.5e-3 * 2048 / 8192 * 2, length=100e3, count=20)
 WORKLOAD = "README advanced channel: 2048^2 grid, delta 1.5 mm, 5 SS screens (MVK, 2^10 rings), 50 km, complex64"
+WORKLOAD_C5 = "long-haul stress: 8192^2 grid, delta 0.75 mm, 20 SS screens (MVK, 2^10 rings), 100 km"
 METRIC = "channel realizations/sec (2048^2, 5 screens)"
 UNIT = "realizations/s"
 
@@ -34,6 +45,38 @@ def measured_peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_source_stamp():
+    """sha1 over the FFT-pass sources: ties profiles/*traffic.json (an ncu capture) to the kernels it was taken from."""
+    h = hashlib.sha1()
+    csrc = os.path.join(ROOT, "pyatmosphere_b200", "csrc")
+    for name in ("fft_core.cuh", "fft_passes.cuh", "fft_tma.cuh", "fft_split.cuh", "fft_inst.inc"):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:12]
+
+
+def ncu_traffic(kernel, batch):
+    """dram bytes per launch from the committed ncu capture, only if it was taken from the kernels as they are now."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("kernel_source_stamp") != kernel_source_stamp():
+            return None, f"profiles/r2_traffic.json is stale (captured at stamp {tj.get('kernel_source_stamp')})"
+        return int(tj[kernel] * batch / tj["batch"]), "ncu --set full capture, profiles/r2_traffic.json"
+    except Exception as e:          # noqa: BLE001
+        return None, f"no capture ({e!r})"
+
+
+def build_channel(pa, p):
+    return pa.Channel(
+        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+        path=pa.IdenticalPhaseScreensPath(
+            phase_screen=pa.SSPhaseScreen(model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
+                                          f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])),
+            length=p["length"], count=p["count"]),
+        pupil=pa.CirclePupil(radius=p["pupil"]))
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -81,7 +124,8 @@ def cpu_cores():
 
 def run_reference(args):
     """`--impl reference`: the reference's CPU algorithm (numpy port in oracle/, pinned against the reference by
-    tests/test_oracle_golden.py) with one realization per worker process per step, on all host cores (capped)."""
+    tests/test_oracle_golden.py, at this very configuration too) with one realization per worker process per step, on
+    all host cores (capped)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -90,14 +134,14 @@ def run_reference(args):
     workers = max(1, min(cores, int(os.environ.get("PYATM_REF_WORKERS", "32"))))
     psd = cpu_psd()
     ctx = mp.get_context("fork")
+    etas = []
     with ctx.Pool(workers, initializer=_cpu_init, initargs=(psd,)) as pool:
-        seed = 0
+        seed = 1                      # seeds 1, 2, 3, ...: the GPU arm replays seeds 1..3 on the same draws (stats_check)
         for _ in range(args.warmup):
             pool.map(_cpu_realization, range(seed, seed + workers))
-            seed += workers
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            pool.map(_cpu_realization, range(seed, seed + workers))
+            etas += pool.map(_cpu_realization, range(seed, seed + workers))
             seed += workers
         dt = time.perf_counter() - t0
     value = workers * args.steps / dt
@@ -110,6 +154,8 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "stats_check": {"seeds": [1, len(etas)], "eta_first3": etas[:3], "mean_eta": float(np.mean(etas)),
+                        "sem_eta": float(np.std(etas, ddof=1) / np.sqrt(len(etas))) if len(etas) > 1 else None},
     }
     print(json.dumps(line))
 
@@ -161,7 +207,6 @@ class ClockSampler:
             self.thread.join(timeout=2)
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable: " + str(self.err)]}
-        nv = self.nv
         busy = [r for r in self.rows if t0 is not None and t0 <= r[2] <= t1] or self.rows[-3:]      # samples inside the timed region
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                  "hw_power_brake_slowdown": 0x80}
@@ -169,29 +214,110 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(r[0] for r in busy), "sm_max_mhz": self.max_sm, "reasons": reasons, "samples": len(busy)}
 
 
+class Dist:
+    """Rank bookkeeping + the barrier / max-over-ranks helpers of the timing contract."""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            import torch.distributed as td
+            td.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.td = td
+
+    def barrier(self):
+        if self.world > 1:
+            self.td.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return float(v)
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.td.all_reduce(t, op=self.td.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.world > 1:
+            self.td.destroy_process_group()
+
+
+def time_pass(lib, h, nat, torch, field, B, kind, turns, leg, wvl, stream, reps=20):
+    for _ in range(3):
+        nat.check(lib.pa_fft_pass(h, nat.ptr(field), B, kind, nat.ptr(turns), leg, wvl, stream))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        nat.check(lib.pa_fft_pass(h, nat.ptr(field), B, kind, nat.ptr(turns), leg, wvl, stream))
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps * 1e-3
+
+
 # ---------------------------------------------------------------------------------------------------------------
-# GPU arm
+# workload c3: the headline line
 # ---------------------------------------------------------------------------------------------------------------
-def run_gpu(args):
+class HostDraws:
+    """Coefficient sets of one step drawn on host threads in the reference's way (grids.py:98-107, phase_screens.py:98-103:
+    one radius fraction per screen, M angles, 2M normals) straight into pinned buffers, `depth` steps ahead of the GPU."""
+
+    def __init__(self, torch, S, B, M, base, psd, seed, depth=3, threads=3):
+        self.S, self.B, self.M = S, B, M
+        self.base = np.asarray(base, dtype=np.float32)
+        self.inner = np.insert(self.base, 0, 0)[:-1]
+        self.amp = np.sqrt(np.asarray(psd, dtype=np.float32))
+        self.sets = [[torch.empty((S, B, M), dtype=torch.float32).pin_memory(), torch.empty((S, B, M), dtype=torch.float32).pin_memory(),
+                      torch.empty((S, B, M, 2), dtype=torch.float32).pin_memory()] for _ in range(depth + 1)]
+        self.rngs = [np.random.default_rng([seed, i]) for i in range(len(self.sets))]
+        self.pool = concurrent.futures.ThreadPoolExecutor(max_workers=threads)
+        self.pending = []
+        self.issued = 0
+        self.draw_seconds = 0.0
+
+    def _draw(self, k):
+        t0 = time.perf_counter()
+        rng = self.rngs[k]
+        fx, fy, cf = (t.numpy() for t in self.sets[k])
+        S, B, M = self.S, self.B, self.M
+        u = rng.random((S, B, 1), dtype=np.float32)
+        rho = np.sqrt(self.inner**2 + u * (self.base**2 - self.inner**2), dtype=np.float32)
+        th = rng.random((S, B, M), dtype=np.float32)
+        th *= np.float32(2 * np.pi)
+        np.multiply(rho, np.cos(th), out=fx)
+        np.multiply(rho, np.sin(th), out=fy)
+        rng.standard_normal(dtype=np.float32, out=cf)
+        cf *= self.amp[:, None]
+        self.draw_seconds += time.perf_counter() - t0
+        return k
+
+    def submit(self):
+        k = self.issued % len(self.sets)
+        self.issued += 1
+        self.pending.append(self.pool.submit(self._draw, k))
+
+    def next(self):
+        """Block until the oldest submitted set is drawn; returns its three pinned tensors."""
+        k = self.pending.pop(0).result()
+        return self.sets[k]
+
+    def close(self):
+        self.pool.shutdown(wait=True)
+
+
+def run_c3(args):
     import torch
     import pyatmosphere_b200 as pa
     from pyatmosphere_b200 import _engine as eng, _native as nat
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        import torch.distributed as td
-        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = Dist()
+    world, rank, local = d.world, d.rank, d.local
     pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method=args.screen_method, theta_cut=None, rng="philox", seed=1234)
     p = C3
-    ch = pa.Channel(
-        grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
-        path=pa.IdenticalPhaseScreensPath(
-            phase_screen=pa.SSPhaseScreen(model=pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"]),
-                                          f_grid=pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])),
-            length=p["length"], count=p["count"]),
-        pupil=pa.CirclePupil(radius=p["pupil"]))
+    ch = build_channel(pa, p)
     ch.path.init_phase_screens()
     ctx = eng.channel_context(ch)
     lib, h = ctx.lib, ctx.handle
@@ -211,12 +337,6 @@ def run_gpu(args):
         nat.check(lib.pa_simulate_batch_device(h, desc.ref(), B, 1234, first + i * B, nat.ptr(edges_d), nat.ptr(psd_d),
                                                nat.ptr(pup_d), 1, nat.ptr(table_d[i]), stride, stream))
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as td
-            td.barrier()
-        torch.cuda.synchronize()
-
     edges = torch.linspace(0, 1, 201, dtype=torch.float64, device=dev)
 
     def reduce_stats(lo, hi):
@@ -225,16 +345,15 @@ def run_gpu(args):
         tab = table_d[lo:hi].reshape(-1, stride)
         hist = torch.zeros(200, dtype=torch.int64, device=dev)
         nat.check(lib.pa_histogram(h, nat.ptr(tab[:, nat.MEASURE_HEAD:]), stride, tab.shape[0], nat.ptr(edges), 200, nat.ptr(hist), stream))
-        sums = torch.stack([tab[:, 1].pow(2).sum(), tab[:, 1].pow(4).sum(), tab[:, 3].sum(), tab[:, 3].pow(2).sum()])
+        sums = torch.stack([tab[:, 1].pow(2).sum(), tab[:, 1].pow(4).sum(), tab[:, 3].sum(), tab[:, 3].pow(2).sum(),
+                            tab[:, nat.MEASURE_HEAD].sum(), tab[:, nat.MEASURE_HEAD].pow(2).sum()])
         if world > 1:
-            import torch.distributed as td
-            td.all_reduce(hist)
-            td.all_reduce(sums)
+            d.td.all_reduce(hist)
+            d.td.all_reduce(sums)
         return hist, sums, tab
 
     # ---- device-resident throughput ------------------------------------------------------------------------
-    # the clock sampler is started BEFORE the warm-up and given time to come up: nvidia-smi's own start-up stalls
-    # kernel launches for tens of milliseconds and must not land inside the timed region
+    # the clock sampler is started BEFORE the warm-up and given time to come up
     sampler = ClockSampler(local)
     if rank == 0 and not os.environ.get("PYATM_BENCH_NOSAMPLER"):
         sampler.start()
@@ -242,145 +361,119 @@ def run_gpu(args):
     for i in range(args.warmup):
         step_device(i)
     reduce_stats(0, args.warmup)          # also warms up the lazily loaded torch / NCCL kernels of the reduction
-    barrier()
+    d.barrier()
     nat.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    d.barrier()
     t_begin = time.perf_counter()
     e0.record()
-    step_events = []
     for i in range(args.steps):
         step_device(args.warmup + i)
-        if os.environ.get("PYATM_BENCH_STEP_TIMES"):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            step_events.append(ev)
     hist, sums, tab = reduce_stats(args.warmup, steps_total)
     e1.record()
-    barrier()
+    d.barrier()
     launches = nat.launch_count()
-    if step_events and rank == 0:
-        ts = [e0.elapsed_time(ev) for ev in step_events]
-        print("per-step ms:", [round(b - a, 2) for a, b in zip([0.0] + ts[:-1], ts)], file=sys.stderr)
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        import torch.distributed as td
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = d.max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
     value = world * args.steps * B / (ms * 1e-3)
+    n_real = world * args.steps * B
+    mean_eta = float(sums[4].item()) / n_real
+    sem_eta = float(np.sqrt(max(float(sums[5].item()) / n_real - mean_eta**2, 0.0) / n_real))
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
-    rng = np.random.default_rng(rank)
-    base = ch.path.phase_screens[0].f_grid.base
-    psd = ch.path.phase_screens[0]._get_psd()
-    inner = np.insert(base, 0, 0)[:-1]
-    n_sets = 4
-
-    def host_set():
-        u = rng.random((S, B, 1), dtype=np.float32)
-        rho = np.sqrt(inner**2 + u * (base**2 - inner**2)).astype(np.float32)
-        th = (2 * np.pi * rng.random((S, B, M))).astype(np.float32)
-        cf = ((rng.standard_normal((S, B, M)) + 1j * rng.standard_normal((S, B, M))).astype(np.complex64) * np.sqrt(psd)).astype(np.complex64)
-        return [torch.from_numpy(a).pin_memory() for a in ((rho * np.cos(th)).astype(np.float32), (rho * np.sin(th)).astype(np.float32),
-                                                           cf.view(np.float32).copy())]
-
-    sets = [host_set() for _ in range(n_sets)]
+    ps0 = ch.path.phase_screens[0]
+    draws = HostDraws(torch, S, B, M, ps0.f_grid.base, ps0._get_psd(), seed=1000 + rank)
     out_host = torch.zeros((B, stride), dtype=torch.float64).pin_memory()
     pup_host = torch.from_numpy(pup).pin_memory()
 
-    def step_e2e(i):
-        fx, fy, cf = sets[i % n_sets]
+    def call_e2e(bufs):
+        fx, fy, cf = bufs
         nat.check(lib.pa_simulate_batch(h, desc.ref(), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), 0, 0, None, None, nat.ptr(pup_host),
                                         1, nat.ptr(out_host), stride, stream))
 
+    def e2e_loop(steps, live):
+        """`live`: every step's coefficients are drawn inside the timed region (host threads, up to 3 steps ahead);
+        otherwise four sets drawn beforehand are cycled (the host side a caller with its own generator would see)."""
+        if live:
+            for _ in range(min(3, steps)):
+                draws.submit()
+        d.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            if live:
+                bufs = draws.next()
+                if i + 3 < steps:
+                    draws.submit()
+            else:
+                bufs = draws.sets[i % len(draws.sets)]
+            call_e2e(bufs)
+        d.barrier()
+        return d.max_over_ranks(time.perf_counter() - t0)
+
+    for k in range(len(draws.sets)):
+        draws._draw(k)
     for i in range(max(1, min(args.warmup, 3))):
-        step_e2e(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step_e2e(i)
-    barrier()
-    dt_e2e = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as td
-        t = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
-        td.all_reduce(t, op=td.ReduceOp.MAX)
-        dt_e2e = float(t.item())
-    e2e_value = world * args.steps * B / dt_e2e
+        call_e2e(draws.sets[i % len(draws.sets)])
+    draws.draw_seconds = 0.0
+    dt_live = e2e_loop(args.steps, live=True)
+    draw_ms = 1e3 * draws.draw_seconds / args.steps
+    dt_pre = e2e_loop(args.steps, live=False)
+    draws.close()
+    e2e_value = world * args.steps * B / dt_live
     h2d = 3 * S * B * M * 4 + S * B * M * 4 + pup.nbytes      # fx, fy (4 B) + coef (8 B) per ring + pupil table
     d2h = B * stride * 8
 
-    # ---- roofline of the FFT passes (algorithmic bytes: 4 N^2 8 B per launch = half a split-step stage) -----
-    roof = None
-    roof_screen = None
-    cpu = None
+    roof = roof_screen = cpu = None
+    stats = {"hist_total": int(hist.sum().item()), "mean_eta": mean_eta, "sem_eta": sem_eta, "realizations": n_real}
     if rank == 0:
-        field = ctx.empty_field(B)
+        # ---- roofline of the FFT passes (algorithmic bytes: 4 N^2 8 B per launch = half a split-step stage) -----
+        Br = 8
+        field = ctx.empty_field(Br)
         field.zero_()
-        turns = torch.rand((B, n, n), dtype=torch.float32, device=dev) - 0.5
+        turns = torch.rand((Br, n, n), dtype=torch.float32, device=dev) - 0.5
         leg = float(ch.path.leg_lengths()[1])
-        reps = 20
-        times = {}
-        for kind, name in ((0, "k_cols"), (1, "k_rows(ifft*screen*fft)")):
-            for _ in range(3):
-                nat.check(lib.pa_fft_pass(h, nat.ptr(field), B, kind, nat.ptr(turns), leg, p["wvl"], stream))
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            torch.cuda.synchronize()
-            a.record()
-            for _ in range(reps):
-                nat.check(lib.pa_fft_pass(h, nat.ptr(field), B, kind, nat.ptr(turns), leg, p["wvl"], stream))
-            b.record()
-            torch.cuda.synchronize()
-            times[name] = a.elapsed_time(b) / reps * 1e-3
+        times = {name: time_pass(lib, h, nat, torch, field, Br, kind, turns, leg, p["wvl"], stream)
+                 for kind, name in ((0, "k_cols"), (1, "k_rows(ifft*screen*fft)"))}
         peak, peak_src = measured_peaks()
-        alg = 4 * n * n * 8 * B
+        alg = 4 * n * n * 8 * Br
         name = max(times, key=times.get)
-        traffic = None
-        try:        # dram bytes per launch of the same kernels from the committed ncu capture (scaled to this batch)
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            traffic = int(tj[name] * B / tj["batch"])
-        except Exception:
-            pass
+        traffic, traffic_src = ncu_traffic(name, Br)
         roof = {"bound": "hbm", "kernel": name, "achieved": alg / times[name] / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg / times[name] / 1e9 / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg,
+                "frac": alg / times[name] / 1e9 / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg, "fields_per_launch": Br,
                 "per_kernel_us": {k: v * 1e6 for k, v in times.items()},
-                "stage_us_per_realization": sum(times.values()) * 1e6 / B,
-                "stage_frac_of_hbm_roofline": (8 * n * n * 8 * B) / sum(times.values()) / 1e9 / peak}
-        # ---- tensor-pipe roofline of the screen synthesis (pa_screen_ss, tcgen05 path): B screens per call, preparation
+                "per_kernel_frac": {k: alg / v / 1e9 / peak for k, v in times.items()},
+                "stage_us_per_realization": sum(times.values()) * 1e6 / Br,
+                "stage_frac_of_hbm_roofline": (8 * n * n * 8 * Br) / sum(times.values()) / 1e9 / peak}
+        # ---- tensor-pipe roofline of the screen synthesis (pa_screen_ss, tcgen05 path): 8 screens per call, preparation
         # kernels included.  Executed MMA flops = 3 split-fp16 products x 2 N^2 K2 (K2 = 2 x high rings, padded to 32);
         # algorithmic flops = 4 N^2 M (SURVEY.md s8d).  Peak = measured dense bf16 cuBLAS throughput (same pipe, same rate).
-        roof_screen = None
         try:
-            ps0 = ch.path.phase_screens[0]
             m_split, degree = ps0.low_ring_plan()
             method = eng.screen_method(n)
             if method == nat.PA_SCREEN_TC:
-                fx_d = torch.empty((B, M), dtype=torch.float32, device=dev)
+                fx_d = torch.empty((Br, M), dtype=torch.float32, device=dev)
                 fy_d = torch.empty_like(fx_d)
-                cf_d = torch.empty((B, M, 2), dtype=torch.float32, device=dev)
-                nat.check(lib.pa_rng_spectrum(h, 99, 0, B, 0, 1, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d),
+                cf_d = torch.empty((Br, M, 2), dtype=torch.float32, device=dev)
+                nat.check(lib.pa_rng_spectrum(h, 99, 0, Br, 0, 1, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d),
                                               nat.ptr(cf_d), stream))
                 bound = eng.coef_bound(ps0._ring_power(), m_split)
 
                 def screens():
-                    nat.check(lib.pa_screen_ss(h, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), M, m_split, degree, 0.0, 0.0, B,
+                    nat.check(lib.pa_screen_ss(h, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), M, m_split, degree, 0.0, 0.0, Br,
                                                nat.ptr(turns), None, 0, method, bound, stream))
                 for _ in range(3):
                     screens()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 a.record()
-                for _ in range(reps):
+                for _ in range(20):
                     screens()
                 b.record()
                 torch.cuda.synchronize()
-                t_scr = a.elapsed_time(b) / reps * 1e-3
+                t_scr = a.elapsed_time(b) / 20 * 1e-3
                 k2 = -(-2 * (M - m_split) // 32) * 32
-                mma_flops = 3 * 2.0 * n * n * k2 * B
+                mma_flops = 3 * 2.0 * n * n * k2 * Br
                 try:
                     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                         tpeak, tsrc = float(json.load(f)["bf16_tflops"]), "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)"
@@ -388,23 +481,37 @@ def run_gpu(args):
                     tpeak, tsrc = 2250.0, "nominal dense bf16 (no MEASURED_PEAKS.json)"
                 roof_screen = {"bound": "tensor", "kernel": "pa_screen_ss (k_factors_tc + polynomial nodes + k_screen_tc)",
                                "achieved": mma_flops / t_scr / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": mma_flops / t_scr / 1e12 / tpeak,
-                               "peak_source": tsrc, "us_per_screen": t_scr * 1e6 / B, "executed_mma_flops_per_screen": mma_flops / B,
+                               "peak_source": tsrc, "us_per_screen": t_scr * 1e6 / Br, "executed_mma_flops_per_screen": mma_flops / Br,
                                "algorithmic_flops_per_screen": 4.0 * n * n * M, "rings_in_contraction": int(M - m_split),
                                "rings_as_polynomial": int(m_split)}
         except Exception as e:          # noqa: BLE001  (an extra, never fatal for the bench line)
             roof_screen = {"error": repr(e)}
-        # ---- CPU baseline: numpy port of the reference, one realization on one core ------------------------
+        del field, turns
+        # ---- CPU baseline: numpy port of the reference, one realization per seed on one core; the SAME seeds are then
+        # replayed on the GPU from the same numpy draws and the transmittances compared (reference's complex64 floor)
         if not args.no_cpu:
             _cpu_init(cpu_psd())
             _cpu_realization(0) if args.cpu_warm else None
+            seeds = list(range(1, 1 + args.cpu_samples))
             t0 = time.perf_counter()
-            for seed in range(1, 1 + args.cpu_samples):
-                _cpu_realization(seed)
+            cpu_eta = [_cpu_realization(seed) for seed in seeds]
             dt = time.perf_counter() - t0
             cpu = {"value": args.cpu_samples / dt, "unit": UNIT, "cores": 1, "kind": "port",
                    "sample": f"{args.cpu_samples} realizations of the same workload (oracle/splitstep.py mode='ref': numpy "
                              "restatement of the reference, pinned by tests/test_oracle_golden.py), single process",
                    "host_cores_available": cpu_cores()}
+            pa.gpu.config.update(rng="numpy")
+            gpu_eta = []
+            for seed in seeds:
+                np.random.seed(seed)
+                rec = eng.simulate_realizations(ch, 0, 1, np.arange(1), [p["pupil"]], [])
+                gpu_eta.append(float(rec[0, len(nat.MEASURE_NAMES)]))
+            pa.gpu.config.update(rng="philox")
+            rel = float(np.max(np.abs(np.array(gpu_eta) - np.array(cpu_eta)) / np.array(cpu_eta)))
+            stats.update({"seeds_replayed": seeds, "cpu_eta": cpu_eta, "gpu_eta_same_draws": gpu_eta, "max_rel_diff": rel,
+                          "tolerance": 5e-3})
+            if not rel < 5e-3:
+                raise AssertionError(f"GPU and CPU-reference transmittances differ on the same draws: {stats}")
 
     if rank == 0:
         line = {
@@ -413,17 +520,180 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "realizations_per_step_per_gpu": B, "screen_method": args.screen_method,
                        "rng": "device Philox4x32-10 (value) / host-drawn coefficients in pinned memory (e2e)",
-                       "l2": f"working set per step {B * (n * n * 12) / 2**20:.0f} MiB of field+screen > 126 MB L2" if B >= 4 else "L2-resident"},
+                       "l2": "inputs larger than L2: every chunk of 8 realizations sweeps 384 MiB of field + screen (126 MB L2)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "api": "pa_simulate_batch (C ABI, host buffers in, per-realization table out)"},
-            "roofline": roof, "roofline_screen": roof_screen, "cpu_baseline": cpu,
-            "stats_check": {"hist_total": int(hist.sum().item()), "mean_eta": float(tab[:, nat.MEASURE_HEAD].mean().item())},
+                    "api": "pa_simulate_batch (C ABI, host buffers in, per-realization table out), coefficients drawn on 3 host "
+                           "threads inside the timed region",
+                    "host_draw_ms_per_step": draw_ms, "value_with_predrawn_coefficients": world * args.steps * B / dt_pre},
+            "roofline": roof, "roofline_screen": roof_screen, "cpu_baseline": cpu, "stats_check": stats,
         }
         print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as td
-        td.destroy_process_group()
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload c4: Simulation([BeamResult, PDTResult]).run(), 6000 realizations, sharded
+# ---------------------------------------------------------------------------------------------------------------
+def run_c4(args):
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import distributed as pdist, _native as nat
+    d = Dist()
+    total = args.total
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method=args.screen_method, theta_cut=None, rng="philox", seed=4242,
+                         batch=64)
+    ch = build_channel(pa, C3)
+
+    def job(count):
+        beam = pa.simulations.BeamResult(ch, max_size=count)
+        pdt = pa.simulations.PDTResult(ch, max_size=count)
+        sim = pa.simulations.Simulation([beam, pdt])
+        sim.run()
+        return beam, pdt, sim
+
+    for _ in range(max(1, args.warmup)):
+        job(16 * d.world)
+    sampler = ClockSampler(d.local)
+    if d.rank == 0:
+        sampler.start()
+        time.sleep(0.2)
+    d.barrier()
+    nat.launch_count(reset=True)
+    t_begin = time.perf_counter()
+    for _ in range(args.steps):
+        beam, pdt, sim = job(total)
+    d.barrier()
+    dt = d.max_over_ranks(time.perf_counter() - t_begin)
+    launches = nat.launch_count()
+    clocks = sampler.stop(t_begin, time.perf_counter()) if d.rank == 0 else None
+    # statistics two ways: from the gathered records (what BeamResult / PDTResult report) and from this rank's share
+    # reduced with ONE all-reduce of [200-bin histogram] + [n, sum, sum of squares] (north_star's final all-reduce)
+    cols = sim.last_columns
+    red = pdist.reduce_statistics(sim.last_local_table.cpu().numpy(), cols, eta_names=[("fixed", C3["pupil"])])
+    hist = pdt.histogram()
+    ok = bool(np.array_equal(red[("hist", ("fixed", C3["pupil"]))], hist)) and all(
+        np.isclose(red[k][0], getattr(beam, k)[0], rtol=1e-12) and np.isclose(red[k][1], getattr(beam, k)[1], rtol=1e-9) for k in ("bw", "lt", "st"))
+    records = np.array([m.data for m in beam.measures] + [pdt.measures[0].data])
+    digest = hashlib.sha1(np.ascontiguousarray(records).tobytes()).hexdigest()
+    if d.rank == 0:
+        value = total * args.steps / dt
+        print(json.dumps({
+            "metric": METRIC + " through Simulation([BeamResult, PDTResult]).run()", "value": value, "unit": UNIT, "n_gpus": d.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
+            "config": {"workload": "config 4: " + WORKLOAD + f"; {total} realizations sharded over the ranks, device RNG keyed by the "
+                       "global realization index, one all-gather of the per-sample table at the end", "timing": "wall clock, max over ranks",
+                       "realizations_per_step": total},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(records.nbytes),
+                    "api": "pyatmosphere.simulations.Simulation.run (device RNG: no per-step input to copy)"},
+            "statistics": {"sigma_bw": beam.bw, "sigma_lt": beam.lt, "w_st": beam.st, "mean_eta": float(np.mean(pdt.measures[0].data)),
+                           "hist_nonzero_bins": int((hist > 0).sum()), "allreduced_statistics_equal_gathered": ok,
+                           "records_sha1": digest},
+        }))
+    assert ok, "all-reduced statistics differ from the statistics of the gathered records"
+    d.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# workload c5: 8192^2, 20 screens, 100 km, complex64 (tensor-core screens) and complex128, batched
+# ---------------------------------------------------------------------------------------------------------------
+def run_c5(args):
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    d = Dist()
+    p = C5
+    n, S, M = p["n"], p["count"], p["m"]
+    stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+    pup = np.array([[np.float32(p["pupil"] ** 2), 0, 0]], dtype=np.float32)
+    peak, peak_src = measured_peaks()
+    out = {}
+    fields = {}
+    clocks = None
+    launches = 0
+    for dtype, B in (("complex64", args.batch), ("complex128", max(1, args.batch // 2))):
+        nat.clear_contexts()
+        torch.cuda.empty_cache()
+        pa.gpu.config.update(use_gpu=True, dtype=dtype, screen_method="auto", theta_cut=None, rng="philox", seed=77)
+        ch = build_channel(pa, p)
+        ch.path.init_phase_screens()
+        ctx = eng.channel_context(ch)
+        lib, h, dev = ctx.lib, ctx.handle, ctx.tdevice
+        desc = ch.path._descriptor((0, 0), through_output=False, from_field=False)
+        edges_d, psd_d = eng.ring_tables(ctx, ch.path.phase_screens[0])
+        pup_d = torch.as_tensor(pup, device=dev)
+        steps_total = args.warmup + args.steps
+        table_d = torch.zeros((steps_total, B, stride), dtype=torch.float64, device=dev)
+        stream = nat.stream_ptr()
+        first = d.rank * steps_total * B
+
+        def step(i):
+            nat.check(lib.pa_simulate_batch_device(h, desc.ref(), B, 77, first + i * B, nat.ptr(edges_d), nat.ptr(psd_d),
+                                                   nat.ptr(pup_d), 1, nat.ptr(table_d[i]), stride, stream))
+        sampler = ClockSampler(d.local)
+        if d.rank == 0 and dtype == "complex64":
+            sampler.start()
+            time.sleep(0.2)
+        for i in range(args.warmup):
+            step(i)
+        d.barrier()
+        nat.launch_count(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_begin = time.perf_counter()
+        e0.record()
+        for i in range(args.steps):
+            step(args.warmup + i)
+        e1.record()
+        d.barrier()
+        ms = d.max_over_ranks(e0.elapsed_time(e1))
+        if dtype == "complex64":
+            launches = nat.launch_count()
+            clocks = sampler.stop(t_begin, time.perf_counter()) if d.rank == 0 else None
+        eta = table_d[args.warmup:, :, 0].mean().item()
+        out[dtype] = {"value": d.world * args.steps * B / (ms * 1e-3), "ms_per_step": ms / args.steps, "realizations_per_step_per_gpu": B,
+                      "screens": "tcgen05 split-fp16" if eng.screen_method(n) == nat.PA_SCREEN_TC else "float64 CUDA cores",
+                      "mean_total_power": eta}
+        if d.rank == 0:
+            # one realization's field on the same coefficients in both precisions (tolerance study), and the pass rooflines
+            fx = torch.empty((S, 1, M), dtype=torch.float32, device=dev)
+            fy, cf = torch.empty_like(fx), torch.empty((S, 1, M, 2), dtype=torch.float32, device=dev)
+            nat.check(lib.pa_rng_spectrum(h, 77, 10**6, 1, 0, S, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), stream))
+            field = ctx.empty_field(1)
+            nat.check(lib.pa_propagate(h, desc.ref(), nat.ptr(field), 1, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), stream))
+            fields[dtype] = field[0].to(torch.complex128).cpu()
+            rdt = torch.float32 if dtype == "complex64" else torch.float64
+            turns = torch.rand((1, n, n), dtype=rdt, device=dev) - 0.5
+            leg = float(ch.path.leg_lengths()[1])
+            esz = 8 if dtype == "complex64" else 16
+            alg = 4 * n * n * esz
+            times = {name: time_pass(lib, h, nat, torch, field, 1, kind, turns, leg, p["wvl"], stream, reps=10)
+                     for kind, name in ((0, "column pass (k_col_outer + k_cols_tma<256> + k_col_outer)"), (1, "k_rows(ifft*screen*fft)"))}
+            out[dtype]["roofline"] = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src, "algorithmic_bytes_per_launch": alg,
+                                      "per_kernel_us": {k: v * 1e6 for k, v in times.items()},
+                                      "per_kernel_frac": {k: alg / v / 1e9 / peak for k, v in times.items()}}
+            del field, turns, fx, fy, cf
+        del table_d
+    if d.rank == 0:
+        a, b = fields["complex64"], fields["complex128"]
+        rel = float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+        c64 = out["complex64"]
+        rl = c64.pop("roofline")
+        name = max(rl["per_kernel_us"], key=rl["per_kernel_us"].get)
+        roof = dict(rl, kernel=name, achieved=rl["algorithmic_bytes_per_launch"] / rl["per_kernel_us"][name] / 1e3,
+                    frac=rl["per_kernel_frac"][name], traffic=None)
+        print(json.dumps({
+            "metric": "channel realizations/sec (8192^2, 20 screens, 100 km)", "value": c64["value"], "unit": UNIT, "n_gpus": d.world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": c64["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
+            "config": {"workload": "config 5: " + WORKLOAD_C5, "realizations_per_step_per_gpu": c64["realizations_per_step_per_gpu"],
+                       "rng": "device Philox4x32-10", "l2": "one 8192^2 complex64 field is 512 MiB > 126 MB L2"},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
+            "complex64": c64, "complex128": out["complex128"],
+            "complex64_vs_complex128_rel_l2": rel, "stated_tolerance_complex64_config5": 2e-5,
+        }))
+    d.close()
 
 
 def main():
@@ -431,7 +701,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4", "c5"])
+    ap.add_argument("--total", type=int, default=6000, help="c4: realizations per Simulation.run()")
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--screen-method", dest="screen_method", default="auto")
     ap.add_argument("--no-cpu", action="store_true")
@@ -442,10 +714,20 @@ def main():
         args.steps = args.steps if args.steps is not None else 2
         args.warmup = args.warmup if args.warmup is not None else 1
         run_reference(args)
-    else:
-        args.steps = args.steps if args.steps is not None else 40
+    elif args.workload == "c4":
+        args.steps = args.steps if args.steps is not None else 1
+        args.warmup = args.warmup if args.warmup is not None else 3
+        run_c4(args)
+    elif args.workload == "c5":
+        args.steps = args.steps if args.steps is not None else 4
         args.warmup = max(3, args.warmup if args.warmup is not None else 3)
-        run_gpu(args)
+        args.batch = args.batch or 4
+        run_c5(args)
+    else:
+        args.steps = args.steps if args.steps is not None else 24
+        args.warmup = max(3, args.warmup if args.warmup is not None else 3)
+        args.batch = args.batch or 160
+        run_c3(args)
 
 
 if __name__ == "__main__":

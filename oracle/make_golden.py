@@ -252,6 +252,52 @@ def case_fft(pa, p, seed):
                         screen0_complex=full0, measures=measures_of(pa, ch, out), versions=_versions(), **params_arrays(p))
 
 
+def case_c3(pa, seeds=(3, 4)):
+    """Config 3 -- the configuration the bench metric is quoted on (README advanced channel: 2048^2, 5 SS screens,
+    50 km) -- run by the UNMODIFIED reference for each seed.  Stored per seed: the exported draws (rho, theta, value),
+    the reference's own measures (measures.py:7-38 on its complex64 output, eta behind the 0.2 m pupil), and a 64 x 64
+    centre crop of its output field.  Next to them the float64 restatement (oracle/splitstep.py mode='f64') on the same
+    draws: its seven moments, eta_pupil and the same crop, so that the GPU box can check the fused Monte-Carlo route
+    without re-running 2048^2 float64 GEMMs for every test (tests that do want the full field run the oracle there)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import splitstep as orc
+    p = dict(n=2048, delta=1.5e-3, wvl=808e-9, w0=0.12, Cn2=5e-16, l0=6e-3, L0=1e3, m=2**10,
+             f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2, length=50e3, count=5, pupil=0.2)
+    ch = build_channel(pa, p)
+    ch.path.init_phase_screens()
+    x, y = orc.rect_xy(p["n"], p["delta"])
+    c0, c1 = p["n"] // 2 - 32, p["n"] // 2 + 32
+    keys = ("eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2", "mean_x2_r")
+    rec = {k: [] for k in ("rho", "theta", "value", "ref_measures", "ref_crop", "f64_measures", "f64_crop", "ref_vs_f64")}
+    for seed in seeds:
+        np.random.seed(seed)
+        rho, theta, value = [], [], []
+        for ps in ch.path.phase_screens:
+            sp = ps._get_spectrum(False)
+            rho.append(np.asarray(sp.rho)); theta.append(np.asarray(sp.theta)); value.append(np.asarray(sp.value))
+        np.random.seed(seed)
+        out = np.asarray(ch.run(pupil=False))
+        rec["rho"].append(np.stack(rho)); rec["theta"].append(np.stack(theta)); rec["value"].append(np.stack(value))
+        rec["ref_measures"].append(measures_of(pa, ch, out))
+        rec["ref_crop"].append(out[c0:c1, c0:c1].copy())
+        screens = []
+        for s in range(p["count"]):
+            fx, fy = orc.spectrum_to_fxy(rho[s], theta[s])
+            screens.append(orc.ss_screen(x, y, fx, fy, value[s], mode="f64"))
+        want = orc.propagate(orc.gaussian_source(x, y, p["w0"], p["wvl"], mode="f64"), screens, p["length"],
+                             orc.screen_positions(p["length"], p["count"]), p["wvl"], p["delta"], mode="f64")
+        m = orc.moments(want, x, y, p["delta"], pupils=[(p["pupil"], (0, 0))], mode="f64")
+        rec["f64_measures"].append(np.array([m[k] for k in keys] + [m["eta_pupil"][0]], dtype=np.float64))
+        rec["f64_crop"].append(want[c0:c1, c0:c1].copy())
+        rec["ref_vs_f64"].append(np.linalg.norm(out - want) / np.linalg.norm(want))
+        print("c3 seed", seed, "reference vs float64 restatement rel-L2", rec["ref_vs_f64"][-1], "eta_pupil", m["eta_pupil"][0])
+    np.savez_compressed(os.path.join(OUT, "c3_2048.npz"), seeds=np.array(seeds), psd=np.asarray(ch.path.phase_screens[0]._get_psd()),
+                        f64_names=np.array(list(keys) + ["eta_pupil"]),
+                        ref_names=np.array(["eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2", "eta_pupil"]),
+                        crop=np.array([c0, c1]), versions=_versions(), **params_arrays(p),
+                        **{k: np.stack(v) for k, v in rec.items()})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     pa = _import_reference()
@@ -273,6 +319,7 @@ def main():
     case_wind_su(pa, dict(small, count=2), seed=17, speed=0.011, calls=3)
     case_fft(pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
                       pupil=0.1, subharmonics=2), seed=13)
+    case_c3(pa)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
@@ -287,5 +334,8 @@ if __name__ == "__main__":
         case_wind_su(_pa, _small, seed=17, speed=0.011, calls=3)
         case_fft(_pa, dict(n=128, delta=4e-3, wvl=808e-9, w0=0.06, Cn2=2e-15, l0=6e-3, L0=1e2, length=6e3, count=2,
                            pupil=0.1, subharmonics=2), seed=13)
+    elif len(sys.argv) > 1 and sys.argv[1] == "--only-c3":    # add the config-3 fixture without touching the others
+        os.makedirs(OUT, exist_ok=True)
+        case_c3(_import_reference())
     else:
         main()

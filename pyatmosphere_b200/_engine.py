@@ -50,6 +50,8 @@ def channel_context(channel) -> nat.Context:
 
 def grid_context(grid) -> nat.Context:
     gpu.require_gpu()
+    if grid.resolution[0] != grid.resolution[1]:
+        raise ValueError("only square grids are supported (the reference's get_f_grid / ifft2 assume it too)")
     return nat.context(grid.resolution[0], grid.delta, grid.get_x(), grid.get_y(), gpu.precision())
 
 
@@ -169,6 +171,13 @@ def _buffers(ctx, batch):
     return buf
 
 
+def uniform_ring_powers(screens) -> bool:
+    """True when every screen of the path has the same ring powers (IdenticalPhaseScreensPath, or a PhaseScreensPath of
+    equal slabs): one table then serves the whole-path device RNG of pa_simulate_batch."""
+    first = screens[0]._get_psd()
+    return all(q._get_psd() is first or np.array_equal(q._get_psd(), first) for q in screens[1:])
+
+
 def ring_tables(ctx, screen):
     """Device copies of the ring edges and ring powers of a screen (inputs of the device RNG)."""
     torch = nat.torch_mod()
@@ -209,7 +218,10 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
     stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
     nm = len(nat.MEASURE_NAMES)
     tab = np.array([[np.float32(r**2), 0, 0] for r in pupils_fixed], dtype=np.float32).reshape(-1, 3)
-    if not pupils_tracked and len(pupils_fixed) <= 4:
+    # the one-call route draws every screen from ONE ring-power table; screens of different thickness / model are drawn
+    # screen by screen below, each from its own table
+    one_table = host is not None or uniform_ring_powers(path.phase_screens)
+    if not pupils_tracked and len(pupils_fixed) <= 4 and one_table:
         # statistics only: one C-ABI call per batch; the library reduces inside the final row pass and never
         # writes the output fields (simulations/simulation.py:89-114 for Beam/PDT records)
         out_host = np.empty((B, stride), dtype=np.float64)
@@ -235,12 +247,13 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
         fy_d = torch.as_tensor(np.ascontiguousarray(host[1][sel].transpose(1, 0, 2)), device=dev)
         cf_d = torch.as_tensor(np.ascontiguousarray(host[2][sel].transpose(1, 0, 2)).view(np.float32), device=dev)
     else:
-        edges_d, psd_d = ring_tables(ctx, path.phase_screens[0])
         fx_d = torch.empty((S, B, M), dtype=torch.float32, device=dev)
         fy_d = torch.empty((S, B, M), dtype=torch.float32, device=dev)
         cf_d = torch.empty((S, B, M, 2), dtype=torch.float32, device=dev)
-        nat.check(ctx.lib.pa_rng_spectrum(ctx.handle, int(gpu.config["seed"]), int(mine[0]), B, 0, S, M, nat.ptr(edges_d),
-                                          nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
+        for s, ps in enumerate(path.phase_screens):       # the records are keyed (seed; realization, screen, ring)
+            edges_d, psd_d = ring_tables(ctx, ps)
+            nat.check(ctx.lib.pa_rng_spectrum(ctx.handle, int(gpu.config["seed"]), int(mine[0]), B, s, 1, M, nat.ptr(edges_d),
+                                              nat.ptr(psd_d), nat.ptr(fx_d[s]), nat.ptr(fy_d[s]), nat.ptr(cf_d[s]), stream))
     nat.check(ctx.lib.pa_propagate(ctx.handle, desc.ref(), nat.ptr(field), B, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), stream))
     tab_d = torch.as_tensor(tab, device=dev) if len(pupils_fixed) else None
     nat.check(ctx.lib.pa_measure(ctx.handle, nat.ptr(field), B, nat.ptr(tab_d), len(pupils_fixed), 0, nat.ptr(table), stride, stream))
@@ -260,3 +273,85 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
         t2 = table2[:B].cpu().numpy()
         out[:, nm + len(pupils_fixed):] = t2[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + len(pupils_tracked)]
     return out
+
+
+class BlockRunner:
+    """Device-RNG Monte-Carlo blocks with NOTHING but kernel launches between the first and the last realization: every
+    batch is enqueued on the current stream (pa_simulate_batch_device, or pa_rng_spectrum + pa_propagate + pa_measure when
+    apertures are tracked / the screens differ), its records land in a device table, and the caller reads that table
+    back ONCE per block (simulations/simulation.py: one gather per save_step / at the end).  Mirrors the per-iteration
+    work of simulations/simulation.py:89-114 for BeamResult / PDTResult / TrackedPDTResult records."""
+
+    def __init__(self, channel, pupils_fixed, pupils_tracked):
+        torch = nat.torch_mod()
+        self.channel, self.path = channel, channel.path
+        self.ctx = channel_context(channel)
+        self.path.init_phase_screens()
+        screens = self.path.phase_screens
+        if not all(getattr(ps, "device_rng", False) for ps in screens):
+            raise ValueError("gpu.config['rng'] = 'philox' draws sparse-spectrum coefficients with fixed ring powers "
+                             "(SSPhaseScreen); use rng = 'numpy' for the other screen generators")
+        if len(pupils_fixed) > nat.MAX_PUPILS or len(pupils_tracked) > nat.MAX_PUPILS:
+            raise ValueError(f"at most {nat.MAX_PUPILS} fixed and {nat.MAX_PUPILS} tracked apertures per simulation")
+        self.fixed, self.tracked = list(pupils_fixed), list(pupils_tracked)
+        self.cols = table_columns(self.fixed, self.tracked)
+        self.S, self.M = len(screens), screens[0].f_grid.points
+        self.desc = self.path._descriptor((0, 0), through_output=False, from_field=False)
+        self.one_call = not self.tracked and uniform_ring_powers(screens)
+        dev = self.ctx.tdevice
+        tab = np.array([[np.float32(r**2), 0, 0] for r in self.fixed], dtype=np.float32).reshape(-1, 3)
+        self.pup_d = torch.as_tensor(tab, device=dev) if len(self.fixed) else None
+        self.r2_tracked = torch.as_tensor(np.array([np.float32(r**2) for r in self.tracked], dtype=np.float32), device=dev)
+        self.stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+        self.ws = None
+
+    def _workspace(self, B):
+        torch = nat.torch_mod()
+        if self.ws is None or self.ws["B"] < B:
+            dev, S, M = self.ctx.tdevice, self.S, self.M
+            self.ws = {"B": B, "field": self.ctx.empty_field(B),
+                       "fx": torch.empty((S, B, M), dtype=torch.float32, device=dev),
+                       "fy": torch.empty((S, B, M), dtype=torch.float32, device=dev),
+                       "cf": torch.empty((S, B, M, 2), dtype=torch.float32, device=dev),
+                       "per": torch.empty((B, max(1, len(self.tracked)), 3), dtype=torch.float32, device=dev)}
+        return self.ws
+
+    def run(self, first: int, count: int):
+        """Enqueue realizations [first, first + count); returns the device table [count][len(cols)] (float64).  No
+        synchronisation, no host copies."""
+        torch = nat.torch_mod()
+        ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.handle
+        dev, stride = ctx.tdevice, self.stride
+        seed, B0 = int(gpu.config["seed"]), max(1, int(gpu.config["batch"]))
+        nm, nf, nt = len(nat.MEASURE_NAMES), len(self.fixed), len(self.tracked)
+        raw = torch.empty((count, stride), dtype=torch.float64, device=dev)
+        raw2 = torch.empty((count, stride), dtype=torch.float64, device=dev) if nt else None
+        stream = nat.stream_ptr()
+        screens = self.path.phase_screens
+        for b0 in range(0, count, B0):
+            B = min(B0, count - b0)
+            if self.one_call:
+                edges_d, psd_d = ring_tables(ctx, screens[0])
+                nat.check(lib.pa_simulate_batch_device(h, self.desc.ref(), B, seed, first + b0, nat.ptr(edges_d), nat.ptr(psd_d),
+                                                       nat.ptr(self.pup_d), nf, nat.ptr(raw[b0:]), stride, stream))
+                continue
+            ws = self._workspace(B0)
+            fx, fy, cf = ws["fx"][:, :B].contiguous(), ws["fy"][:, :B].contiguous(), ws["cf"][:, :B].contiguous()
+            for s, ps in enumerate(screens):                  # records are keyed (seed; realization, screen, ring)
+                edges_d, psd_d = ring_tables(ctx, ps)
+                nat.check(lib.pa_rng_spectrum(h, seed, first + b0, B, s, 1, self.M, nat.ptr(edges_d), nat.ptr(psd_d),
+                                              nat.ptr(fx[s]), nat.ptr(fy[s]), nat.ptr(cf[s]), stream))
+            field = ws["field"]
+            nat.check(lib.pa_propagate(h, self.desc.ref(), nat.ptr(field), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), stream))
+            nat.check(lib.pa_measure(h, nat.ptr(field), B, nat.ptr(self.pup_d), nf, 0, nat.ptr(raw[b0:]), stride, stream))
+            if nt:
+                # aperture re-centred on each realization's centroid: shift = (mean_x, mean_y) (simulations/pdt.py:62-66)
+                per = ws["per"][:B]
+                per[:, :, 0] = self.r2_tracked
+                per[:, :, 1] = raw[b0:b0 + B, 1].to(torch.float32)[:, None]
+                per[:, :, 2] = raw[b0:b0 + B, 2].to(torch.float32)[:, None]
+                nat.check(lib.pa_measure(h, nat.ptr(field), B, nat.ptr(per), nt, 1, nat.ptr(raw2[b0:]), stride, stream))
+        parts = [raw[:, :nm], raw[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + nf]]
+        if nt:
+            parts.append(raw2[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + nt])
+        return torch.cat(parts, dim=1)

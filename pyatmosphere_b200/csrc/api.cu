@@ -87,7 +87,8 @@ struct pa_ctx {
     double* polyc = nullptr; size_t polyc_bytes = 0;
     double* partials = nullptr; size_t partials_bytes = 0;
     void* field = nullptr; size_t field_bytes = 0;
-    float* spec = nullptr; size_t spec_bytes = 0;        // fx | fy | coef staging for pa_simulate_batch
+    float* spec = nullptr; size_t spec_bytes = 0;        // fx | fy | coef staging of one chunk of pa_simulate_batch
+    float* spec_all = nullptr; size_t spec_all_bytes = 0;   // host coefficients of a whole multi-chunk batch
     float* pupils = nullptr; size_t pupils_bytes = 0;
     double* table = nullptr; size_t table_bytes = 0;
     std::vector<TensorMapEntry> tmaps;   // column-pass tensor maps, keyed by (field pointer, batch)
@@ -582,7 +583,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
 int pa_ctx_destroy(pa_ctx* c) {
     if (!c) return PA_OK;
     cudaSetDevice(c->device);
-    void* ptrs[] = {c->x, c->y, c->tw, c->tw_sub, c->otw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums, c->perm_dev, c->fftws};
+    void* ptrs[] = {c->x, c->y, c->tw, c->tw_sub, c->otw, c->turns, c->P, c->Q, c->polyc, c->partials, c->field, c->spec, c->spec_all, c->pupils, c->table, c->tcws, c->tc_err, c->rowsums, c->perm_dev, c->fftws};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (auto& h : c->htabs) {
@@ -945,32 +946,25 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
     return propagate_impl(c, p, field, batch, fx, fy, coef, stream, nullptr);
 }
 
-static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host,
-                           const float* coef_host, unsigned long long seed, unsigned long long realization0,
-                           const float* edges, const float* psd, const float* pupils_dev, int npupil, double* table_dev,
-                           int out_stride, cudaStream_t st) {
-    const int S = p->n_screens, m = p->m, n = c->n;
-    int rc = grow(&c->field, &c->field_bytes, (size_t)batch * n * n * c->csize());
-    if (rc) return rc;
-    const size_t cnt = (size_t)batch * (S > 0 ? S : 1) * m;
-    rc = grow((void**)&c->spec, &c->spec_bytes, cnt * 4 * sizeof(float));
-    if (rc) return rc;
-    float* fx = c->spec;
-    float* fy = c->spec + cnt;
-    float* coef = c->spec + 2 * cnt;
-    if (S > 0) {
-        if (coef_host) {
-            PA_CUDA(cudaMemcpyAsync(fx, fx_host, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
-            PA_CUDA(cudaMemcpyAsync(fy, fy_host, cnt * sizeof(float), cudaMemcpyHostToDevice, st));
-            PA_CUDA(cudaMemcpyAsync(coef, coef_host, cnt * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
-        } else {
-            rc = pa_rng_spectrum(c, seed, realization0, batch, 0, S, m, edges, psd, fx, fy, coef, st);
-            if (rc) return rc;
-        }
-    }
+// Realizations per pass of the fused path inside pa_simulate_batch*: a batch of any size is processed in chunks of this
+// many realizations (8 at 2048^2: 384 MiB of field + screen, larger than L2, and enough CTAs to fill the machine several
+// times over; more at smaller grids, where launch overhead would show; fewer at the long-haul sizes).  PYATM_SIM_CHUNK
+// overrides.
+static int sim_chunk(const pa_ctx* c) {
+    static const int forced = getenv("PYATM_SIM_CHUNK") ? atoi(getenv("PYATM_SIM_CHUNK")) : 0;
+    if (forced > 0) return forced;
+    const long long want = 8LL * 2048 * 2048 / ((long long)c->n * c->n);
+    return (int)(want < 2 ? 2 : (want > 64 ? 64 : want));
+}
+
+// one chunk: coefficients already on the device, [S][batch][m] contiguous
+static int simulate_chunk(pa_ctx* c, const pa_path* p, int batch, const float* fx, const float* fy, const float* coef,
+                          const float* pupils_dev, int npupil, double* table_dev, int out_stride, cudaStream_t st) {
+    const int n = c->n;
     // statistics only: reduce inside the final row pass and do not write the output field at all
     FusedMeasure fm{nullptr, pupils_dev, npupil, 0, false};
     FusedMeasure* fmp = nullptr;
+    int rc;
     if (npupil <= kFusedPupils && !(getenv("PYATM_NO_FUSED_MEASURE") && atoi(getenv("PYATM_NO_FUSED_MEASURE")) != 0)) {
         rc = grow((void**)&c->rowsums, &c->rowsums_bytes, (size_t)batch * n * kRowSums * sizeof(double));
         if (rc) return rc;
@@ -986,6 +980,55 @@ static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* 
                             "measure (fused)");
     }
     return pa_measure(c, c->field, batch, pupils_dev, npupil, 0, table_dev, out_stride, st);
+}
+
+static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host,
+                           const float* coef_host, unsigned long long seed, unsigned long long realization0,
+                           const float* edges, const float* psd, const float* pupils_dev, int npupil, double* table_dev,
+                           int out_stride, cudaStream_t st) {
+    const int S = p->n_screens, m = p->m, n = c->n;
+    const int chunk = std::min(batch, sim_chunk(c));
+    int rc = grow(&c->field, &c->field_bytes, (size_t)chunk * n * n * c->csize());
+    if (rc) return rc;
+    const size_t rows = (size_t)(S > 0 ? S : 1);
+    const size_t cnt = (size_t)chunk * rows * m;            // staging of one chunk: fx | fy | coef
+    rc = grow((void**)&c->spec, &c->spec_bytes, cnt * 4 * sizeof(float));
+    if (rc) return rc;
+    float* fx = c->spec;
+    float* fy = c->spec + cnt;
+    float* coef = c->spec + 2 * cnt;
+    const float* all_fx = nullptr;
+    if (S > 0 && coef_host) {
+        const size_t all = (size_t)batch * rows * m;
+        if (batch == chunk) {
+            PA_CUDA(cudaMemcpyAsync(fx, fx_host, all * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(fy, fy_host, all * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(coef, coef_host, all * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        } else {
+            // the whole batch travels host -> device once; every chunk is then gathered into the contiguous staging
+            rc = grow((void**)&c->spec_all, &c->spec_all_bytes, all * 4 * sizeof(float));
+            if (rc) return rc;
+            all_fx = c->spec_all;
+            PA_CUDA(cudaMemcpyAsync(c->spec_all, fx_host, all * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(c->spec_all + all, fy_host, all * sizeof(float), cudaMemcpyHostToDevice, st));
+            PA_CUDA(cudaMemcpyAsync(c->spec_all + 2 * all, coef_host, all * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+    }
+    for (int c0 = 0; c0 < batch; c0 += chunk) {
+        const int b = std::min(chunk, batch - c0);
+        if (S > 0 && coef_host && all_fx) {
+            const size_t all = (size_t)batch * rows * m, spitch = (size_t)batch * m * sizeof(float), w = (size_t)b * m * sizeof(float);
+            PA_CUDA(cudaMemcpy2DAsync(fx, w, all_fx + (size_t)c0 * m, spitch, w, rows, cudaMemcpyDeviceToDevice, st));
+            PA_CUDA(cudaMemcpy2DAsync(fy, w, all_fx + all + (size_t)c0 * m, spitch, w, rows, cudaMemcpyDeviceToDevice, st));
+            PA_CUDA(cudaMemcpy2DAsync(coef, 2 * w, all_fx + 2 * all + (size_t)c0 * m * 2, 2 * spitch, 2 * w, rows, cudaMemcpyDeviceToDevice, st));
+        } else if (S > 0 && !coef_host) {
+            rc = pa_rng_spectrum(c, seed, realization0 + (unsigned long long)c0, b, 0, S, m, edges, psd, fx, fy, coef, st);
+            if (rc) return rc;
+        }
+        rc = simulate_chunk(c, p, b, fx, fy, coef, pupils_dev, npupil, table_dev + (size_t)c0 * out_stride, out_stride, st);
+        if (rc) return rc;
+    }
+    return PA_OK;
 }
 
 int pa_simulate_batch(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,

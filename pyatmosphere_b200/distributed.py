@@ -58,6 +58,31 @@ def gather_rows(local: np.ndarray, local_rows: np.ndarray, total_rows: int) -> n
     return full.cpu().numpy()
 
 
+def all_gather_blocks(local, counts) -> np.ndarray:
+    """Concatenate every rank's block of rows, rank 0 first: [sum(counts)][C] float64 on the host of EVERY rank.
+
+    `local` is this rank's block -- a torch tensor (CUDA under NCCL: the block goes device -> NVLink -> device and is read
+    back once) or a numpy array; `counts[r]` is the number of rows rank r owns.  One collective per call: this is the only
+    communication of a Monte-Carlo block (all-gather of the per-sample scalar table, a few hundred KB)."""
+    world, rank = world_rank()
+    counts = [int(c) for c in counts]
+    if world == 1:
+        return np.asarray(local.detach().cpu().numpy() if hasattr(local, "detach") else local, dtype=np.float64)
+    import torch
+    td = _td()
+    dev = _comm_device()
+    t = local if hasattr(local, "detach") else torch.as_tensor(np.asarray(local, dtype=np.float64))
+    t = t.to(device=dev, dtype=torch.float64)
+    assert t.shape[0] == counts[rank], (t.shape, counts, rank)
+    width, top = t.shape[1], max(counts)
+    padded = torch.zeros((top, width), dtype=torch.float64, device=dev)
+    padded[:t.shape[0]] = t
+    parts = [torch.empty_like(padded) for _ in range(world)]
+    td.all_gather(parts, padded)
+    host = torch.stack(parts).cpu().numpy()
+    return np.concatenate([host[r, :counts[r]] for r in range(world)], axis=0)
+
+
 def allreduce_sum(values) -> np.ndarray:
     """Sum an integer histogram or a vector of float64 moment sums over all ranks."""
     world, _ = world_rank()

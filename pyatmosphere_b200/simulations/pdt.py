@@ -41,22 +41,25 @@ class PDTResult(Result):
         return self.measures[-len(self.pupils):]
 
     def plot_output(self):
+        """Transmittance histograms, one panel per aperture, drawn from `histogram()` (the counts the statistics use)."""
         from matplotlib import pyplot as plt
-        pm = self.pdt_measures()
-        if len(self.pupils) == 1:
-            plt.hist(pm[0].data, label=f"Count: {len(pm[0])}", bins=self.bins_single, range=(0, 1))
-            plt.legend()
-            plt.show()
-            return
-        n_x = 3
-        n_y = len(self.pupils) // n_x + bool(len(self.pupils) % n_x)
-        fig, axes = plt.subplots(n_y, n_x, figsize=(15, 3 * n_y))
-        for i, ax in enumerate(axes.flat):
-            if i >= len(self.pupils):
-                break
-            ax.hist(pm[i].data, label=f"Pupil radius: {self.pupils[i].radius:.3f}\nCount: {len(pm[0])}",
-                    bins=self.bins_multi, range=(0, 1))
-            ax.legend()
+        records = self.pdt_measures()
+        panels = len(records)
+        columns = min(panels, 3)
+        rows = -(-panels // columns)
+        fig, axes = plt.subplots(rows, columns, figsize=(5 * columns, 3 * rows), squeeze=False)
+        for index, axis in enumerate(axes.ravel()):
+            if index >= panels:
+                axis.set_visible(False)
+                continue
+            counts = self.histogram(index)
+            edges = np.linspace(0.0, 1.0, len(counts) + 1)
+            caption = f"Count: {len(records[index])}"
+            if panels > 1:
+                caption = f"Pupil radius: {self.pupils[index].radius:.3f}\n" + caption
+            axis.stairs(counts, edges, fill=True, label=caption)
+            axis.set_xlim(0.0, 1.0)
+            axis.legend()
         plt.show()
 
 

@@ -46,11 +46,14 @@ class SIResult(Result):
         return np.mean(samples * samples, axis=0) / (mean * mean) - 1
 
     def plot_output(self):
+        """Scintillation index against distance, with whichever closed-form curves were registered."""
         from matplotlib import pyplot as plt
-        plt.plot(self.positions, self.si, label=r"On-axis SI $\sigma_I$, m")
-        for curve, f in zip(self.theoretical_si, self.theoretical_functions):
-            plt.plot(self.positions, curve, label=f"Theoretical on-axis SI: {f.__name__}")
-        plt.plot(np.nan, np.nan, label=f"Iterations: {len(self.measures[0])}", alpha=0)
-        plt.xlabel("Propagation distance z, m")
-        plt.legend()
+        z = self.positions
+        fig, axis = plt.subplots()
+        axis.plot(z, self.si, marker="o", label=f"simulated on-axis scintillation index ({len(self.measures[0])} iterations)")
+        for function, curve in zip(self.theoretical_functions, self.theoretical_si):
+            axis.plot(z, curve, linestyle="--", label=f"theory: {function.__name__}")
+        axis.set_xlabel("z, m")
+        axis.set_ylabel("scintillation index")
+        axis.legend()
         plt.show()

@@ -3,12 +3,14 @@
 Two execution routes give the same records:
   * the generic route (`iter`) follows the reference step by step -- channel.generator per realization, every
     Measure's operations applied to a copy of the output -- and serves arbitrary user operations;
-  * the batched route (`iter_batch`) is taken by `run` when every Measure is one of the known reductions
-    (BeamResult / PDTResult / TrackedPDTResult records): `gpu.config['batch']` realizations are propagated by one
-    fused call and reduced by one sweep.  With `gpu.config['rng'] == 'numpy'` the spectra are drawn from
-    numpy's global RNG in the reference's order, so the records equal the generic route's for the same seed;
-    with 'philox' they are drawn on the device, keyed by the realization index, and realizations are sharded
-    over the ranks of an initialised torch.distributed group (see ..distributed).
+  * the batched route is taken by `run` when every Measure is one of the known reductions (BeamResult / PDTResult /
+    TrackedPDTResult records): `gpu.config['batch']` realizations are propagated by one fused call and reduced by one
+    sweep.  With `gpu.config['rng'] == 'numpy'` (`iter_batch`) the spectra are drawn from numpy's global RNG in the
+    reference's order, so the records equal the generic route's for the same seed.  With 'philox' (`iter_block`) they
+    are drawn on the device, keyed by the global realization index: a whole block of realizations -- everything up to
+    the next plot / save step, or to the end -- is cut into one contiguous share per rank of the torch.distributed
+    group, each rank enqueues its share batch after batch with no host round trip, and the block ends with ONE
+    all-gather of the per-sample table (see ..distributed), so every rank appends identical records in index order.
 """
 from __future__ import annotations
 
@@ -34,6 +36,13 @@ class Simulation:
         for result in results_list or []:
             for m in result.measures:
                 self.add_measures(m)
+        self._resume_counter()
+
+    def _resume_counter(self):
+        """Records loaded from a CSV checkpoint (Result.load_output) were drawn with device-RNG indices 0..L-1: continue
+        after them, otherwise a resumed 'philox' run would replay the same realizations and store duplicate samples."""
+        done = max((len(m) for m in self.flattened_measures()), default=0)
+        self.realizations_done = max(self.realizations_done, done)
 
     # ---- measure tree: channel -> time -> measure_type -> operations -> [Measure] (simulation.py:19-30) ------
     def add_measures(self, m):
@@ -141,14 +150,52 @@ class Simulation:
                 m.data.append(float(table[r, cols[name]]))
         self.realizations_done += count
 
+    def iter_block(self, count):
+        """`count` device-RNG realizations: this rank's contiguous share runs with nothing but kernel launches in between
+        (engine BlockRunner), then one all-gather hands every rank the whole table."""
+        channel = next(iter(self.measures))
+        ms = list(self.flattened_measures())
+        pupils_fixed = sorted({m.fast_key[1] for m in ms if m.fast_key[0] == "pupil_eta" and m.fast_key[2] == "fixed"})
+        pupils_tracked = sorted({m.fast_key[1] for m in ms if m.fast_key[0] == "pupil_eta" and m.fast_key[2] == "tracked"})
+        key = (id(channel), tuple(pupils_fixed), tuple(pupils_tracked), gpu.config["dtype"], gpu.config["screen_method"],
+               gpu.config["theta_cut"])
+        if getattr(self, "_runner_key", None) != key:
+            self._runner, self._runner_key = eng.BlockRunner(channel, pupils_fixed, pupils_tracked), key
+        world, rank = dist.world_rank()
+        first = self.realizations_done
+        shares = [len(b) for b in np.array_split(np.arange(count), world)]
+        mine_first = first + sum(shares[:rank])
+        local = self._runner.run(mine_first, shares[rank])
+        self.last_local_table, self.last_columns = local, self._runner.cols        # this rank's share (device), for reductions
+        table = dist.all_gather_blocks(local, shares)
+        cols = self._runner.cols
+        for m in ms:
+            if m.is_done:
+                continue
+            key = m.fast_key
+            name = key[1] if key[0] == "moment" else (key[2], key[1])
+            take = count if m.max_size is None else min(count, m.max_size - len(m))
+            m.data.extend(table[:take, cols[name]].tolist())
+        self.realizations_done += count
+
     # ---- driver (simulation.py:127-152) ----------------------------------------------------------------------
     def run(self, *args, plot_step: int = None, save_step: int = None, **kwargs):
         gpu.require_gpu()
+        self._resume_counter()
         try:
             iteration = 0
             use_batch = self.batchable() and gpu.config["batch"] > 1
+            use_block = self.batchable() and gpu.config["rng"] != "numpy"
             while not self.is_measures_done():
-                if use_batch:
+                if use_block:
+                    left = self.remaining()
+                    count = left if left is not None else 64 * gpu.config["batch"] * dist.world_rank()[0]
+                    for step in (plot_step, save_step):      # a block never steps across a multiple of the plot / save step
+                        if step:
+                            count = min(count, step - iteration % step)
+                    self.iter_block(count)
+                    iteration += count
+                elif use_batch:
                     left = self.remaining()
                     count = gpu.config["batch"] * dist.world_rank()[0]
                     count = count if left is None else min(count, left)

@@ -46,6 +46,15 @@ class SourceField(DeviceArray):
         self._t = value
 
 
+class PlaneSource(Source):
+    """Unit-amplitude plane wave (sources.py:16-18).  The reference returns the scalar 1, which none of its paths accepts
+    (SURVEY.md App. B); here it is the field of ones on the channel grid, which they do."""
+
+    def output(self):
+        ctx = eng.channel_context(self.channel)
+        return DeviceArray(nat.torch_mod().ones((ctx.n, ctx.n), dtype=ctx.cdtype, device=ctx.tdevice))
+
+
 class GaussianSource(GaussianBeam, Source):
     """sqrt(2/pi)/w0 exp(-(1/w0^2 + i k/(2 F0)) rho^2) on the channel grid (sources.py:21-23 ->
     theory/sources.py:16-18), produced by pa_source_gaussian."""

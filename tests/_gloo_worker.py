@@ -18,6 +18,13 @@ full[:, cols["mean_x"]] -= 0.5
 mine = dist.shard_indices(0, total, rank, world)
 gathered = dist.gather_rows(full[mine], mine, total)
 assert np.array_equal(gathered, full)
+# one all-gather of unequal per-rank blocks (the end-of-block collective of Simulation.iter_block), numpy and torch inputs
+shares = [len(b) for b in np.array_split(np.arange(total), world)]
+start = sum(shares[:rank])
+block = full[start:start + shares[rank]]
+assert np.array_equal(dist.all_gather_blocks(block, shares), full)
+import torch
+assert np.array_equal(dist.all_gather_blocks(torch.as_tensor(block), shares), full)
 stats = dist.reduce_statistics(full[mine], cols, eta_names=[("fixed", 0.1)])
 bw2 = full[:, cols["mean_x"]] ** 2
 lt2 = 4 * full[:, cols["mean_x2"]]

@@ -15,6 +15,30 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def _gpu_unavailable():
+    """Reason why `-m gpu` tests cannot run here, or None.  (On the B200 box both conditions hold; a plain `pytest` on a
+    CPU box then skips the GPU tests instead of failing them.)"""
+    lib = os.path.join(ROOT, "pyatmosphere_b200", "libpyatm_b200.so")
+    if not os.path.exists(lib):
+        return "libpyatm_b200.so is not built (python -m pyatmosphere_b200.build)"
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return "no CUDA device"
+    except ImportError:
+        return "torch is not importable"
+    return None
+
+
+def pytest_collection_modifyitems(config, items):
+    reason = None
+    for item in items:
+        if "gpu" in item.keywords:
+            reason = reason if reason is not None else (_gpu_unavailable() or "")
+            if reason:
+                item.add_marker(pytest.mark.skip(reason=reason))
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         d = {k: z[k] for k in z.files}

@@ -1,0 +1,257 @@
+"""Round-2 GPU tests of the host routes around the hot path: the reference's README run verbatim through the
+`pyatmosphere` import name, the block route of Simulation.run (device-side accumulation, one gather per block), resume of
+a device-RNG run, and paths whose screens carry different ring powers."""
+import sys
+import types
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from test_gpu_parity import build_channel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _cfg():
+    import pyatmosphere_b200 as pa
+    saved = dict(pa.gpu.config)
+    yield
+    pa.gpu.config.clear()
+    pa.gpu.config.update(saved)
+
+
+class _Axis:
+    def __init__(self, log):
+        self._log = log
+
+    def __getattr__(self, name):
+        def call(*args, **kwargs):
+            self._log.append((name, args, kwargs))
+        return call
+
+
+def _fake_matplotlib(monkeypatch):
+    """matplotlib is not installed on the box: a recording stand-in (plotting itself is out of scope)."""
+    log = []
+    plt = types.ModuleType("matplotlib.pyplot")
+
+    def subplots(rows=1, cols=1, squeeze=True, **kwargs):
+        axes = np.empty((rows, cols), dtype=object)
+        for i in range(rows):
+            for j in range(cols):
+                axes[i, j] = _Axis(log)
+        log.append(("subplots", (rows, cols), kwargs))
+        return object(), (axes[0, 0] if squeeze and rows * cols == 1 else axes)
+
+    plt.subplots = subplots
+    for name in ("imshow", "hist", "plot", "legend", "show", "xlabel", "ylabel", "title", "figure", "colorbar"):
+        setattr(plt, name, getattr(_Axis(log), name))
+    root = types.ModuleType("matplotlib")
+    root.pyplot = plt
+    monkeypatch.setitem(sys.modules, "matplotlib", root)
+    monkeypatch.setitem(sys.modules, "matplotlib.pyplot", plt)
+    return log
+
+
+README_GPU = """
+from pyatmosphere import gpu
+gpu.config['use_gpu'] = True
+"""
+README_QUICK = """
+from pyatmosphere import QuickChannel
+
+quick_channel = QuickChannel(
+    Cn2=1e-15,
+    length=10000,
+    count_ps=5,
+    beam_w0=0.09,
+    beam_wvl=8.08e-07,
+    aperture_radius=0.12
+    )
+
+quick_channel.plot()
+"""
+README_ADVANCED = """
+import numpy as np
+from pyatmosphere import (
+    Channel,
+    RectGrid,
+    RandLogPolarGrid,
+    GaussianSource,
+    IdenticalPhaseScreensPath,
+    SSPhaseScreen,
+    CirclePupil,
+    MVKModel,
+    measures
+    )
+
+channel = Channel(
+    grid=RectGrid(
+        resolution=2048,
+        delta=0.0015
+    ),
+    source=GaussianSource(
+        wvl=808e-9,
+        w0=0.12,
+        F0=np.inf
+    ),
+    path=IdenticalPhaseScreensPath(
+        phase_screen=SSPhaseScreen(
+            model=MVKModel(
+                Cn2=5e-16,
+                l0=6e-3,
+                L0=1e3,
+            ),
+            f_grid=RandLogPolarGrid(
+                points=2**10,
+                f_min=1 / 1e3 / 15,
+                f_max=1 / 6e-3 * 2
+            )
+        ),
+        length=50e3,
+        count=5
+    ),
+    pupil=CirclePupil(
+        radius=0.2
+    ),
+)
+
+channel_output = channel.run(pupil=False)
+intensity = measures.I(channel, output=channel_output)
+mean_x = measures.mean_x(channel, output=channel_output)
+"""
+README_SIM = """
+from pyatmosphere import simulations
+
+beam_result = simulations.BeamResult(quick_channel, max_size=2000)
+pdt_result = simulations.PDTResult(quick_channel, max_size=6000)
+sim = simulations.Simulation([beam_result, pdt_result])
+sim.run(plot_step=1000)
+"""
+
+
+def test_reference_readme_runs_verbatim(monkeypatch):
+    """The four usage snippets of the reference's README.md (:26-29, :33-46, :50-97, :100-106), executed as written
+    against the `pyatmosphere` import name of this tree.  Config 3's seed-3 records tie the advanced-channel snippet to
+    the reference's own output; the simulation snippet reproduces the statistics the reference's notebook recorded."""
+    log = _fake_matplotlib(monkeypatch)
+    ns = {}
+    exec(README_GPU, ns)
+    exec(README_QUICK, ns)
+    shown = [e for e in log if e[0] == "imshow"]
+    assert len(shown) == 1 and shown[0][1][0].shape == (1024, 1024) and shown[0][2]["extent"] == ns["quick_channel"].grid.extent
+    g = load_golden("c3_2048")
+    np.random.seed(int(g["seeds"][0]))
+    exec(README_ADVANCED, ns)
+    assert ns["channel_output"].shape == (2048, 2048) and ns["intensity"].shape == (2048, 2048)
+    ref = dict(zip([str(k) for k in g["ref_names"]], g["ref_measures"][0]))
+    f64 = dict(zip([str(k) for k in g["f64_names"]], g["f64_measures"][0]))
+    assert ns["mean_x"] == pytest.approx(f64["mean_x"], rel=1e-4, abs=1e-7)
+    assert ns["mean_x"] == pytest.approx(ref["mean_x"], rel=2e-2, abs=2e-5)
+    assert float(ns["intensity"].sum().item()) * 0.0015**2 == pytest.approx(1.0, abs=2e-5)
+    np.random.seed(2023)
+    exec(README_SIM, ns)
+    beam, pdt = ns["beam_result"], ns["pdt_result"]
+    assert len(beam.measures[0]) == 2000 and len(pdt.measures[0]) == 6000
+    assert sum(1 for e in log if e[0] == "stairs") == 7          # plot_step=1000 -> 6 plots + the closing one
+    for key, (ref_v, ref_err, half_digit) in {"bw": (3.9e-2, 6.2e-4, 0.05e-2), "lt": (1.8e-1, 6.8e-4, 0.05e-1),
+                                              "st": (1.6e-1, 4.3e-4, 0.05e-1)}.items():      # main.ipynb:252-254
+        val, err = getattr(beam, key)
+        assert abs(val - ref_v) < 4 * np.hypot(err, ref_err) + half_digit, (key, val, err)
+    assert pdt.histogram().sum() == 6000
+
+
+def _records(result_list):
+    return np.array([m.data for r in result_list for m in r.measures])
+
+
+def test_block_route_equals_batch_route_and_is_sync_free():
+    """Simulation.run in device-RNG mode accumulates on the device and gathers once; its records equal the per-batch
+    engine route (simulate_realizations) for the same global indices, for fixed and for tracked apertures."""
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact", theta_cut=2.0, rng="philox", seed=5, batch=4)
+    p = load_golden("turb128")["params"]
+    ch = build_channel(pa, p)
+    beam = pa.simulations.BeamResult(ch, max_size=9)
+    pdt = pa.simulations.PDTResult(ch, pupils=[pa.CirclePupil(0.1), pa.CirclePupil(0.03)], max_size=11)
+    trk = pa.simulations.TrackedPDTResult(ch, pupils=[pa.CirclePupil(0.05)], max_size=11)
+    sim = pa.simulations.Simulation([beam, pdt, trk])
+    calls = []
+    real = pa.distributed.all_gather_blocks
+    pa.distributed.all_gather_blocks = lambda local, counts: calls.append(tuple(counts)) or real(local, counts)
+    try:
+        sim.run()
+    finally:
+        pa.distributed.all_gather_blocks = real
+    assert calls == [(11,)]                                     # one gather for the whole run
+    assert len(beam.measures[0]) == 9 and len(pdt.measures[1]) == 11 and sim.realizations_done == 11
+    cols = eng.table_columns([0.03, 0.1], [0.05])
+    want = eng.simulate_realizations(ch, 0, 11, np.arange(11), [0.03, 0.1], [0.05])
+    assert np.array_equal(np.asarray(beam.measures[0].data), want[:9, cols["mean_x"]])
+    assert np.array_equal(np.asarray(pdt.measures[0].data), want[:, cols[("fixed", 0.1)]])
+    assert np.array_equal(np.asarray(pdt.measures[1].data), want[:, cols[("fixed", 0.03)]])
+    assert np.array_equal(np.asarray(trk.measures[2].data), want[:, cols[("tracked", 0.05)]])
+    # save_step cuts the run into blocks; the records do not change
+    pdt2 = pa.simulations.PDTResult(ch, pupils=[pa.CirclePupil(0.1)], max_size=11)
+    pa.simulations.Simulation([pdt2]).run(save_step=4)
+    assert np.array_equal(np.asarray(pdt2.measures[0].data), want[:, cols[("fixed", 0.1)]])
+
+
+def test_resumed_device_rng_run_draws_new_realizations(tmp_path):
+    """resuming from a CSV checkpoint in 'philox' mode must not replay indices 0..L-1."""
+    import pyatmosphere_b200 as pa
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact", theta_cut=2.0, rng="philox", seed=8, batch=4)
+    p = load_golden("turb128")["params"]
+    ch = build_channel(pa, p)
+    full = pa.simulations.PDTResult(ch, max_size=10)
+    pa.simulations.Simulation([full]).run()
+    path = str(tmp_path / "pdt.csv")
+    part = pa.simulations.PDTResult(ch, max_size=6, save_path=path)
+    part.save_float_format = lambda v: "%.17e" % v                        # keep the checkpoint lossless for the comparison
+    pa.simulations.Simulation([part]).run(save_step=3)
+    again = pa.simulations.PDTResult(ch, max_size=10, save_path=path)
+    assert len(again.measures[0]) == 6
+    sim = pa.simulations.Simulation([again])
+    assert sim.realizations_done == 6
+    sim.run()
+    data = np.asarray(again.measures[0].data)
+    assert len(set(data.tolist())) == 10                                   # no duplicate samples
+    assert np.array_equal(data, np.asarray(full.measures[0].data))         # == the uninterrupted run
+
+
+def test_device_rng_uses_each_screens_own_ring_powers():
+    """a PhaseScreensPath of unequal slabs in 'philox' mode -- every screen is drawn from its own table."""
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact", theta_cut=2.0, rng="philox", seed=3, batch=4)
+    p = load_golden("turb128")["params"]
+    model = pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])
+    fg = pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])
+    thin, thick = pa.SSPhaseScreen(model=model, f_grid=fg, thickness=1e3), pa.SSPhaseScreen(model=model, f_grid=fg, thickness=3e3)
+    ch = pa.Channel(grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+                    path=pa.PhaseScreensPath(length=4e3, phase_screens=[thin, thick], positions=[5e2, 2.5e3]),
+                    pupil=pa.CirclePupil(radius=p["pupil"]))
+    pdt = pa.simulations.PDTResult(ch, max_size=4)
+    sim = pa.simulations.Simulation([pdt])
+    sim.run()
+    assert not sim._runner.one_call
+    # restated by hand: per-screen draws from per-screen tables, literal propagation, separate measure sweep
+    ctx = eng.channel_context(ch)
+    S, M, B = 2, p["m"], 4
+    fx = torch.empty((S, B, M), dtype=torch.float32, device="cuda")
+    fy, cf = torch.empty_like(fx), torch.empty((S, B, M, 2), dtype=torch.float32, device="cuda")
+    for s, ps in enumerate((thin, thick)):
+        e_d, p_d = eng.ring_tables(ctx, ps)
+        nat.check(ctx.lib.pa_rng_spectrum(ctx.handle, 3, 0, B, s, 1, M, nat.ptr(e_d), nat.ptr(p_d), nat.ptr(fx[s]), nat.ptr(fy[s]),
+                                          nat.ptr(cf[s]), nat.stream_ptr()))
+    amp = (cf[..., 0] ** 2 + cf[..., 1] ** 2).mean(dim=1).cpu().numpy()       # E|c|^2 = 2 psd per ring
+    assert np.median(amp[1] / amp[0]) == pytest.approx(3.0, rel=0.35)        # thick slab: three times the ring powers
+    field = ctx.empty_field(B)
+    desc = ch.path._descriptor((0, 0), through_output=False, from_field=False)
+    nat.check(ctx.lib.pa_propagate(ctx.handle, desc.ref(), nat.ptr(field), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), nat.stream_ptr()))
+    etas = [pa.measures.eta(ch, output=ch.pupil.output(pa.gpu.DeviceArray(field[i]))) for i in range(B)]
+    assert np.allclose(pdt.measures[0].data, etas, rtol=1e-6)

@@ -3,7 +3,8 @@ path, and end-to-end field parity with it switched on (the default for complex64
 
 Stated tolerances for the tensor-core method (README advanced channel, theta_cut = 10):
   phase error vs float64: rms <= 5e-6 rad, max <= 6e-5 rad per screen;
-  complex64 field after 5 screens vs float64 oracle / complex128 path: relative L2 <= 2e-5.
+  complex64 field after 5 screens vs float64 oracle / complex128 path: relative L2 <= 1e-5 (the north-star tolerance;
+  the direct comparison with the oracle at config 3 is tests/test_gpu_c3_parity.py).
 """
 import numpy as np
 import pytest
@@ -106,7 +107,9 @@ def test_channel_run_with_tc_screens(name):
     np.random.seed(int(g["seed"]))
     out = ch.run(pupil=False).get()
     want, _ = oracle_field(g, "f64")
-    assert rel_l2(out, want) < 2e-5
+    err = rel_l2(out, want)
+    print(f"quick channel on 1024^2, tensor-core screens vs float64 oracle: rel-L2 {err:.3e}")
+    assert err < 1e-5
 
 
 def test_full_size_tc_vs_complex128():
@@ -121,7 +124,9 @@ def test_full_size_tc_vs_complex128():
         out = ch.run(pupil=False)
         assert pa.measures.eta(ch, output=out) == pytest.approx(1.0, abs=2e-5)
         fields[dtype] = out.get()
-    assert rel_l2(fields["complex64"], fields["complex128"]) < 2e-5
+    err = rel_l2(fields["complex64"], fields["complex128"])
+    print(f"config 3, tensor-core complex64 vs complex128: rel-L2 {err:.3e}")
+    assert err < 1e-5
 
 
 def test_single_cta_kernel_matches_oracle_in_a_subprocess():

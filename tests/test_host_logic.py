@@ -336,3 +336,83 @@ def test_c_abi_rejects_null_arguments_with_a_status_code():
     assert b"unsupported" in lib.pa_last_error()
     with pytest.raises(nat.NativeError):
         nat.check(1)
+
+
+# ---- round-2 host logic -----------------------------------------------------------------------------------------------
+def test_pyatmosphere_import_name_is_a_true_alias():
+    """README.md:26-28,100 / main.ipynb import lines resolve against this tree: the `pyatmosphere` package re-exports the
+    modules of pyatmosphere_b200 under the reference's module paths (same objects, no second copy of any state)."""
+    import importlib
+    import pyatmosphere
+    from pyatmosphere import gpu, QuickChannel, simulations, measures          # noqa: F401
+    from pyatmosphere import (Channel, RectGrid, RandLogPolarGrid, GaussianSource, IdenticalPhaseScreensPath,    # noqa: F401
+                              SSPhaseScreen, CirclePupil, MVKModel)
+    from pyatmosphere.simulations import BeamResult, PDTResult, Simulation      # noqa: F401
+    assert gpu.config is pa.gpu.config and simulations is pa.simulations
+    for name in ("channels", "grids", "pathes", "phase_screens", "pupils", "sources", "utils", "measures", "gpu",
+                 "simulations.beam", "simulations.pdt", "simulations.simulation", "simulations.result", "simulations.measure",
+                 "simulations.si", "simulations.wind", "theory.models", "theory.sources", "theory.atmosphere"):
+        assert importlib.import_module("pyatmosphere." + name) is importlib.import_module("pyatmosphere_b200." + name), name
+    ns = {}
+    exec("from pyatmosphere import *", ns)
+    assert sorted(k for k in ns if not k.startswith("__")) == ["Channel", "QuickChannel"]      # __init__.py:14-17
+    assert pyatmosphere.PlaneSource is pa.PlaneSource
+    ch = QuickChannel(Cn2=1e-15, length=10000, count_ps=5, beam_w0=0.09, beam_wvl=8.08e-07, aperture_radius=0.12)
+    assert ch.grid.resolution[0] == 1024 and len(ch.path.phase_screens) == 5
+
+
+def test_resume_continues_the_device_rng_counter(tmp_path):
+    """A Result resumed from its CSV checkpoint holds L records drawn with device-RNG indices 0..L-1: the Simulation must
+    continue at index L (it restarted at 0 and stored duplicate samples)."""
+    p = load_golden("turb128")["params"]
+    ch = _channel(p)
+    path = str(tmp_path / "beam.csv")
+    beam = pa.simulations.BeamResult(ch, max_size=10, save_path=path)
+    for i, m in enumerate(beam.measures):
+        m.data = [0.1 * (i + 1)] * 4
+    beam.save_output()
+    again = pa.simulations.BeamResult(ch, max_size=10, save_path=path)
+    pdt = pa.simulations.PDTResult(ch, max_size=10)
+    sim = pa.simulations.Simulation([again, pdt])
+    assert sim.realizations_done == 4
+    assert pa.simulations.Simulation([pdt]).realizations_done == 0
+
+
+def test_non_square_grid_is_rejected_before_any_native_call():
+    from pyatmosphere_b200 import gpu
+    assert gpu.config["use_gpu"]
+    with pytest.raises(ValueError, match="square"):
+        eng.grid_context(pa.RectGrid((128, 256), 1e-3))
+
+
+def test_reference_style_screen_subclass_still_generates():
+    """A user subclass written against the reference's contract (generate_phase_screen returns the complex screen and
+    knows nothing about real_only, phase_screens.py:21-28) keeps working through PhaseScreen.generate."""
+    class Ramp(pa.phase_screens.PhaseScreen):
+        def generate_phase_screen(self, gain=1.0):
+            return gain * (np.arange(6).reshape(2, 3) + 1j * np.ones((2, 3)))
+
+    scr = Ramp(model=None)
+    assert np.array_equal(scr.generate(), np.arange(6).reshape(2, 3))
+    assert np.array_equal(scr.generate(gain=2.0), 2.0 * np.arange(6).reshape(2, 3))
+    assert np.iscomplexobj(scr.generate(complex=True))
+    gen = scr.generator()
+    assert np.array_equal(next(gen), np.arange(6).reshape(2, 3)) and np.array_equal(next(gen), np.ones((2, 3)))
+
+
+def test_uniform_ring_powers_detects_unequal_slabs():
+    """The device RNG of pa_simulate_batch draws every screen from ONE ring-power table: only valid when all screens of
+    the path carry the same powers."""
+    p = load_golden("turb128")["params"]
+    ch = _channel(p)
+    ch.path.init_phase_screens()
+    assert eng.uniform_ring_powers(ch.path.phase_screens)
+    model = pa.MVKModel(Cn2=p["Cn2"], l0=p["l0"], L0=p["L0"])
+    fg = pa.RandLogPolarGrid(points=p["m"], f_min=p["f_min"], f_max=p["f_max"])
+    thin, thick = pa.SSPhaseScreen(model=model, f_grid=fg, thickness=1e3), pa.SSPhaseScreen(model=model, f_grid=fg, thickness=3e3)
+    ch2 = pa.Channel(grid=pa.RectGrid(resolution=p["n"], delta=p["delta"]), source=pa.GaussianSource(wvl=p["wvl"], w0=p["w0"], F0=np.inf),
+                     path=pa.PhaseScreensPath(length=4e3, phase_screens=[thin, thick], positions=[5e2, 2.5e3]),
+                     pupil=pa.CirclePupil(radius=p["pupil"]))
+    ch2.path.init_phase_screens()
+    assert ch2.path._fusable() and not eng.uniform_ring_powers(ch2.path.phase_screens)
+    assert np.allclose(thick._get_psd(), 3 * thin._get_psd(), rtol=1e-5)
