@@ -130,12 +130,12 @@ template <typename T> static int build_twiddles(int n, int e, void** out) {
     const int total = plan_tw_size(n, e);
     std::vector<cplx<T>> tw((size_t)(total > 0 ? total : 1));
     for (int s = 0; s + 1 < L; ++s) {
-        const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s), nb = n / R, off = plan_tw_off(n, e, s);
+        const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s), off = plan_tw_off(n, e, s);
         for (int j = 1; j < R; ++j)
-            for (int b = 0; b < nb; ++b) {
-                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j * (long double)(b % sigma) /
+            for (int b = 0; b < sigma; ++b) {
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * (long double)j * (long double)b /
                                         (long double)(sigma * R);
-                tw[(size_t)off + (size_t)(j - 1) * nb + b] = mkc<T>((T)cosl(ang), (T)sinl(ang));
+                tw[(size_t)off + (size_t)(j - 1) * sigma + b] = mkc<T>((T)cosl(ang), (T)sinl(ang));
             }
     }
     PA_CUDA(cudaMalloc(out, tw.size() * sizeof(cplx<T>)));
@@ -157,17 +157,16 @@ template <typename T> static int build_outer_twiddles(int n, int r0, void** out)
 }
 
 // perm[q] = frequency (numpy fft index) stored at index q of a spectrum.  Register idx of thread t holds, after
-// the last forward stage, position p = base_{L-1}(t, g) + j (idx = g R + j), whose frequency is the mixed-radix
-// digit reversal of p; it is stored at q = t + idx * (n/e)  (fft_core.cuh: io_pos).
+// the last forward stage, position p = RL * plan_last_butterfly(t, g) + j (idx = g RL + j), whose frequency is the
+// mixed-radix digit reversal of p; it is stored at q = t + idx * (n/e)  (fft_core.cuh: io_pos).
 static std::vector<int> storage_perm(int n, int e) {
     const int L = plan_len(n, e), tpf = n / e;
-    const int RL = plan_radix(n, e, L - 1), SL = plan_sigma(n, e, L - 1);
+    const int RL = plan_radix(n, e, L - 1);
     std::vector<int> perm((size_t)n, -1);
     for (int t = 0; t < tpf; ++t)
         for (int idx = 0; idx < e; ++idx) {
             const int g = idx / RL, j = idx % RL;
-            const int b = t + g * tpf;
-            const int p = (b / SL) * (SL * RL) + (b % SL) + j * SL;
+            const int p = plan_last_butterfly(n, e, t, g) * RL + j;
             int k = 0, mult = 1;
             for (int s = 0; s < L; ++s) {
                 const int R = plan_radix(n, e, s), sigma = plan_sigma(n, e, s);

@@ -13,6 +13,12 @@
 // Between stages the E registers go through shared memory (write at stage-s positions, one barrier, read at
 // stage-(s+1) positions).  Because every stage reads exactly the positions it later writes, one barrier per
 // exchange is enough.
+//
+// LAST STAGE (SIGMA = 1): its butterflies are handed out differently (plan_last_butterfly) -- thread t takes the ones that
+// lie inside the blocks of SIGMA_(L-2) * R_(L-2) positions it already works on in stage L-2.  Such a block is shared by
+// R_(L-1) CONSECUTIVE threads, so the exchange between the last two stages never leaves a group of R_(L-1) adjacent
+// threads: when that group sits inside one warp the exchange needs __syncwarp() only (Addr::kLocalLast), which removes
+// two of the four barriers of a 3-stage transform pair (forward + inverse).
 #pragma once
 #include "common.cuh"
 
@@ -32,13 +38,28 @@ __host__ __device__ constexpr int plan_len(int n, int e) {
     while (plan_rem(n, e, s) > 1) ++s;
     return s;
 }
-// offset (in complex elements) of stage s inside the concatenated twiddle table; stage L-1 has none
+// offset (in complex elements) of stage s inside the concatenated twiddle table; stage L-1 has none.  Stage s holds
+// (R-1) * SIGMA entries: the factor of output j of butterfly b is W^(j * (b % SIGMA)), stored at (j-1) * SIGMA + b % SIGMA
+// (compact: threads that share b % SIGMA read the same 8 bytes, one wavefront instead of two per warp-wide load).
 __host__ __device__ constexpr int plan_tw_off(int n, int e, int s) {
     int off = 0;
-    for (int u = 0; u < s; ++u) off += (plan_radix(n, e, u) - 1) * (n / plan_radix(n, e, u));
+    for (int u = 0; u < s; ++u) off += (plan_radix(n, e, u) - 1) * plan_sigma(n, e, u);
     return off;
 }
 __host__ __device__ constexpr int plan_tw_size(int n, int e) { return plan_tw_off(n, e, plan_len(n, e) - 1); }
+
+// Butterfly of the LAST stage (SIGMA = 1, radix RL) that thread t works on as its g-th (g < E / RL):
+// with R' = radix of stage L-2 (whose SIGMA is RL), G' = E / R' blocks per thread there and H = R' / RL butterflies per
+// thread and block:  g = g' H + h,  bt = t + g' (N/E),  b = R' (bt / RL) + bt % RL + RL h.   (L = 1: b = t + g N/E.)
+__host__ __device__ constexpr int plan_last_butterfly(int n, int e, int t, int g) {
+    const int L = plan_len(n, e);
+    if (L < 2) return t + g * (n / e);
+    const int rl = plan_radix(n, e, L - 1), rp = plan_radix(n, e, L - 2);
+    const int gp_count = e / rp, h_count = (e / rl) / gp_count;
+    const int gp = g / h_count, h = g % h_count;
+    const int bt = t + gp * (n / e);
+    return rp * (bt / rl) + (bt % rl) + rl * h;
+}
 
 template <int N, int E, int S> struct Stage {
     static constexpr int R = plan_radix(N, E, S);
@@ -47,9 +68,14 @@ template <int N, int E, int S> struct Stage {
     static constexpr int TPF = N / E;  // threads per transform
     static constexpr int NB = N / R;   // butterflies per transform
     static constexpr int TW = plan_tw_off(N, E, S);
+    static constexpr bool LAST = S == plan_len(N, E) - 1;
     __device__ static __forceinline__ int base(int t, int g) {
-        const int b = t + g * TPF;
-        return (b / SIGMA) * (SIGMA * R) + (b % SIGMA);
+        if constexpr (LAST) {
+            return plan_last_butterfly(N, E, t, g) * R;
+        } else {
+            const int b = t + g * TPF;
+            return (b / SIGMA) * (SIGMA * R) + (b % SIGMA);
+        }
     }
 };
 
@@ -171,7 +197,7 @@ template <typename T, int N, int E, int S> __device__ __forceinline__ void stage
         for (int g = 0; g < St::G; ++g) {
             const int b = t + g * St::TPF;
 #pragma unroll
-            for (int j = 1; j < St::R; ++j) v[g * St::R + j] = cmul(v[g * St::R + j], ldg_c<T>(tw + St::TW + (j - 1) * St::NB + b));
+            for (int j = 1; j < St::R; ++j) v[g * St::R + j] = cmul(v[g * St::R + j], ldg_c<T>(tw + St::TW + (j - 1) * St::SIGMA + b % St::SIGMA));
         }
     }
 }
@@ -183,7 +209,7 @@ template <typename T, int N, int E, int S> __device__ __forceinline__ void stage
         for (int g = 0; g < St::G; ++g) {
             const int b = t + g * St::TPF;
 #pragma unroll
-            for (int j = 1; j < St::R; ++j) v[g * St::R + j] = cmulc(v[g * St::R + j], ldg_c<T>(tw + St::TW + (j - 1) * St::NB + b));
+            for (int j = 1; j < St::R; ++j) v[g * St::R + j] = cmulc(v[g * St::R + j], ldg_c<T>(tw + St::TW + (j - 1) * St::SIGMA + b % St::SIGMA));
         }
     }
     dft_groups<T, St::R, true, St::G, E>(v);
@@ -243,8 +269,13 @@ __device__ __forceinline__ void smem_get(cplx<T> (&v)[E], int t, const cplx<T>* 
 }
 template <typename T, int N, int E, int SA, int SB, typename Addr>
 __device__ __forceinline__ void exchange(cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
+    constexpr int L = plan_len(N, E);
     smem_put<T, N, E, SA>(v, t, sm, addr);
-    addr.sync();
+    if constexpr (Addr::kLocalLast && (SA == L - 1 || SB == L - 1)) {
+        __syncwarp();           // between the last two stages data stays inside groups of R_(L-1) adjacent threads of one warp
+    } else {
+        addr.sync();
+    }
     smem_get<T, N, E, SB>(v, t, sm, addr);
 }
 

@@ -27,12 +27,13 @@ namespace pa {
 // 1 < SIGMA < 16: a half warp needs 16 distinct slots -> the thread bits above SIGMA enter the free slot bits.
 // Sources are always bits above the targets, so every map is a bijection of [0, N).
 template <int N, int E> __device__ __forceinline__ int swz_row(int p) {
+    // (found with tools/bank_sim2.py for the last-stage thread assignment of fft_core.cuh: plan_last_butterfly)
     if constexpr (E == 16 && N == 1024) {           // 16.16.4, SIGMA = 64, 4, 1
-        return p ^ (((p >> 6) & 3) << 2) ^ (((p >> 4) & 1) << 1);
+        return p ^ (((p >> 6) & 1) << 1) ^ (((p >> 5) & 7) << 1);
     } else if constexpr (E == 16 && (N == 4096 || N == 256)) {   // last radix 16, SIGMA = .., 16, 1
         return p ^ (((p >> 4) & 7) << 1);
     } else if constexpr (E == 16 && (N == 8192 || N == 512)) {   // .., 8, 4 with SIGMA = .., 4, 1
-        return p ^ (((p >> 5) & 3) << 2) ^ (((p >> 4) & 1) << 1);
+        return p ^ (((p >> 5) & 1) << 1) ^ (((p >> 4) & 7) << 1);
     } else {
         // 2048 = 16.16.8: bits 1-2 <- bits 4-5 (SIGMA = 1, 16-byte chunks), bit 3 <- bit 7 (SIGMA = 8)
         return p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3);
@@ -62,6 +63,9 @@ template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
 template <int N, int E> struct RowAddr {
     static constexpr bool kContiguous = true;
     static constexpr int TPF = N / E;
+    // the R_last adjacent threads that exchange between the last two stages always share a warp (rows start at multiples
+    // of TPF, R_last divides TPF and 32)
+    static constexpr bool kLocalLast = plan_len(N, E) >= 2;
     int base;
     __device__ __forceinline__ int operator()(int p) const { return base + swz_row<N, E>(p); }
     __device__ __forceinline__ void sync() const {
@@ -79,6 +83,8 @@ template <int N, int E> struct RowAddr {
 };
 template <int N, int E, int TC> struct ColAddr {
     static constexpr bool kContiguous = false;
+    // thread index = c + TC * t: the R_last adjacent t of all TC columns are R_last * TC consecutive threads
+    static constexpr bool kLocalLast = plan_len(N, E) >= 2 && plan_radix(N, E, plan_len(N, E) - 1) * TC <= 32;
     int c;
     __device__ __forceinline__ int operator()(int p) const { return swz_col<N, E, TC>(p) * TC + c; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
