@@ -70,8 +70,12 @@ template <int N, int E, int S> struct Stage {
     static constexpr int TW = plan_tw_off(N, E, S);
     static constexpr bool LAST = S == plan_len(N, E) - 1;
     __device__ static __forceinline__ int base(int t, int g) {
-        if constexpr (LAST) {
-            return plan_last_butterfly(N, E, t, g) * R;
+        if constexpr (LAST && plan_len(N, E) >= 2) {
+            // plan_last_butterfly with every plan quantity folded at compile time (the generic function is for the host)
+            constexpr int RP = plan_radix(N, E, plan_len(N, E) - 2);
+            constexpr int H = (E / R) / (E / RP);
+            const int bt = t + (g / H) * TPF;
+            return (RP * (bt / R) + (bt % R) + R * (g % H)) * R;
         } else {
             const int b = t + g * TPF;
             return (b / SIGMA) * (SIGMA * R) + (b % SIGMA);
@@ -231,52 +235,59 @@ template <int N, int E, int S> __device__ __forceinline__ int reg_pos(int t, int
 // A stage with SIGMA == 1 owns runs of R consecutive positions: with a contiguous address map (rows) and
 // complex64 data these are moved as 128-bit accesses (two elements), which is what the row swizzle is
 // conflict-free for (tools/bank_sim.py).
-template <typename T, int N, int E, int S, typename Addr>
+// Addresses.  Every address map is  position -> (XOR swizzle that is GF(2)-linear in the bits of the position), and the
+// position of register idx of thread t splits into a thread part reg_pos(t, 0) and a register part reg_pos(0, idx) on
+// DISJOINT bits, so  addr(t, idx) = swz(thread part) ^ swz(register part)  with the second factor a compile-time constant
+// K.  Addr::at<S>(t, idx) returns it as  (A_t ^ (K & low)) + (K & ~low)  where `low` are the bits a swizzle may write: the
+// few distinct low parts cost one LOP3 each per exchange and everything else folds into the immediate offset of the
+// LDS / STS, instead of 16 separately computed (and register-resident) addresses per exchange.
+// at<S, LOCAL>: LOCAL marks the warp-local exchange between the last two stages; maps with kDualLayout use a layout of its
+// own there (ColAddrDual, fft_tma.cuh), all others ignore it.
+template <typename T, int N, int E, int S, bool LOCAL, typename Addr>
 __device__ __forceinline__ void smem_put(const cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
     using St = Stage<N, E, S>;
     if constexpr (Addr::kContiguous && St::SIGMA == 1 && sizeof(cplx<T>) == 8 && St::R % 2 == 0) {
 #pragma unroll
-        for (int g = 0; g < St::G; ++g) {
-            const int base = St::base(t, g);
-#pragma unroll
-            for (int j = 0; j < St::R; j += 2)
-                *reinterpret_cast<float4*>(sm + addr(base + j)) =
-                    make_float4(v[g * St::R + j].x, v[g * St::R + j].y, v[g * St::R + j + 1].x, v[g * St::R + j + 1].y);
-        }
+        for (int i = 0; i < E; i += 2)
+            *reinterpret_cast<float4*>(sm + addr.template at<S, LOCAL>(t, i)) = make_float4(v[i].x, v[i].y, v[i + 1].x, v[i + 1].y);
     } else {
 #pragma unroll
-        for (int i = 0; i < E; ++i) sm[addr(reg_pos<N, E, S>(t, i))] = v[i];
+        for (int i = 0; i < E; ++i) sm[addr.template at<S, LOCAL>(t, i)] = v[i];
     }
 }
-template <typename T, int N, int E, int S, typename Addr>
+template <typename T, int N, int E, int S, bool LOCAL, typename Addr>
 __device__ __forceinline__ void smem_get(cplx<T> (&v)[E], int t, const cplx<T>* sm, const Addr& addr) {
     using St = Stage<N, E, S>;
     if constexpr (Addr::kContiguous && St::SIGMA == 1 && sizeof(cplx<T>) == 8 && St::R % 2 == 0) {
 #pragma unroll
-        for (int g = 0; g < St::G; ++g) {
-            const int base = St::base(t, g);
-#pragma unroll
-            for (int j = 0; j < St::R; j += 2) {
-                const float4 q = *reinterpret_cast<const float4*>(sm + addr(base + j));
-                v[g * St::R + j] = mkc<T>(q.x, q.y);
-                v[g * St::R + j + 1] = mkc<T>(q.z, q.w);
-            }
+        for (int i = 0; i < E; i += 2) {
+            const float4 q = *reinterpret_cast<const float4*>(sm + addr.template at<S, LOCAL>(t, i));
+            v[i] = mkc<T>(q.x, q.y);
+            v[i + 1] = mkc<T>(q.z, q.w);
         }
     } else {
 #pragma unroll
-        for (int i = 0; i < E; ++i) v[i] = sm[addr(reg_pos<N, E, S>(t, i))];
+        for (int i = 0; i < E; ++i) v[i] = sm[addr.template at<S, LOCAL>(t, i)];
     }
 }
 template <typename T, int N, int E, int SA, int SB, typename Addr>
 __device__ __forceinline__ void exchange(cplx<T> (&v)[E], int t, cplx<T>* sm, const Addr& addr) {
     constexpr int L = plan_len(N, E);
-    smem_put<T, N, E, SA>(v, t, sm, addr);
-    if constexpr (Addr::kLocalLast && (SA == L - 1 || SB == L - 1)) {
+    // LOCAL: the exchange between the last two stages when its R_(L-1) adjacent threads share a warp
+    constexpr bool LOCAL = Addr::kLocalLast && (SA == L - 1 || SB == L - 1);
+    if constexpr (Addr::kDualLayout && L >= 3 && SA == L - 2) {
+        // dual-layout address maps keep the local exchange in a layout of its own: this thread's previous read of its
+        // stage-(L-2) positions used the other layout, whose addresses (inside the same block of the same R_(L-1) threads)
+        // the writes below may hit -- let every lane of the group finish that read first
+        __syncwarp();
+    }
+    smem_put<T, N, E, SA, LOCAL>(v, t, sm, addr);
+    if constexpr (LOCAL) {
         __syncwarp();           // between the last two stages data stays inside groups of R_(L-1) adjacent threads of one warp
     } else {
         addr.sync();
     }
-    smem_get<T, N, E, SB>(v, t, sm, addr);
+    smem_get<T, N, E, SB, LOCAL>(v, t, sm, addr);
 }
 
 // ---- whole transforms on registers ------------------------------------------------------------------------

@@ -34,26 +34,30 @@ template <int N, int E> __device__ __forceinline__ int swz_row(int p) {
         return p ^ (((p >> 4) & 7) << 1);
     } else if constexpr (E == 16 && (N == 8192 || N == 512)) {   // .., 8, 4 with SIGMA = .., 4, 1
         return p ^ (((p >> 5) & 1) << 1) ^ (((p >> 4) & 7) << 1);
-    } else {
+    } else if constexpr (E == 16) {
         // 2048 = 16.16.8: bits 1-2 <- bits 4-5 (SIGMA = 1, 16-byte chunks), bit 3 <- bit 7 (SIGMA = 8)
         return p ^ (((p >> 4) & 3) << 1) ^ (((p >> 7) & 1) << 3);
+    } else if constexpr (N == 512 || N == 4096) {   // complex128 (E = 8, 16-byte elements: 8 per bank row), radices 8.8.(8.)8
+        return p ^ ((p >> 3) & 7);
+    } else if constexpr (N == 1024 || N == 8192) {  // 8.8.(8.)4.4
+        return p ^ ((p >> 4) & 1) ^ (((p >> 3) & 3) << 1);
+    } else {                                        // 256 = 8.8.4, 2048 = 8.8.8.4
+        return p ^ ((p >> 4) & 3) ^ ((p >> 3) & 7);
     }
 }
-// Columns: a tile keeps TC columns interleaved, so a half warp covers 16/TC consecutive threads of one transform;
-// in the last stage (SIGMA = 1) they sit R_last positions apart -> their bits are folded onto the low bits.
+// Columns: a tile keeps TC columns interleaved, so a half warp (quarter warp for complex128) covers 16/TC (8/TC) consecutive
+// threads of one transform; in the last stage (SIGMA = 1) thread t owns runs of R_last positions that start at multiples of
+// R_last -> those bits are folded onto the low bits.  Every other stage is conflict-free in the natural order.
 template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
-    if constexpr (E == 16) {
-        constexpr int RL = plan_radix(N, E, plan_len(N, E) - 1);
-        constexpr int W = TC >= 16 ? 0 : 4 - ilog2(TC);
-        if constexpr (W == 0) {
-            return p;
-        } else if constexpr (N == 8192 && TC == 1) {            // SIGMA = 4 stage as well: bit 6 -> bit 2
-            return p ^ ((p >> 2) & 15) ^ (((p >> 6) & 1) << 2);
-        } else {
-            return p ^ ((p >> ilog2(RL)) & ((1 << W) - 1));
-        }
+    constexpr int RL = plan_radix(N, E, plan_len(N, E) - 1);
+    constexpr int SLOTS = E == 16 ? 4 : 3;          // log2 of the elements per 128-byte bank row
+    constexpr int W = ilog2(TC) >= SLOTS ? 0 : SLOTS - ilog2(TC);
+    if constexpr (W == 0) {
+        return p;
+    } else if constexpr (E == 16 && N == 8192 && TC == 1) {            // SIGMA = 4 stage as well: bit 6 -> bit 2
+        return p ^ ((p >> 2) & 15) ^ (((p >> 6) & 1) << 2);
     } else {
-        return p ^ ((p >> 3) & 3);
+        return p ^ ((p >> ilog2(RL)) & ((1 << W) - 1));
     }
 }
 
@@ -66,8 +70,15 @@ template <int N, int E> struct RowAddr {
     // the R_last adjacent threads that exchange between the last two stages always share a warp (rows start at multiples
     // of TPF, R_last divides TPF and 32)
     static constexpr bool kLocalLast = plan_len(N, E) >= 2;
+    static constexpr bool kDualLayout = false;
+    static constexpr int kLow = E == 16 ? 0xE : 0xF;       // bits the row swizzles write (complex64 keeps 16-byte pairs intact)
     int base;
     __device__ __forceinline__ int operator()(int p) const { return base + swz_row<N, E>(p); }
+    template <int S, bool LOCAL> __device__ __forceinline__ int at(int t, int idx) const {
+        const int vt = swz_row<N, E>(reg_pos<N, E, S>(t, 0));
+        const int k = swz_row<N, E>(reg_pos<N, E, S>(0, idx));          // compile-time constant once unrolled
+        return base + ((vt ^ (k & kLow)) + (k & ~kLow));
+    }
     __device__ __forceinline__ void sync() const {
 #ifndef PA_ROW_BLOCK_BARRIER
         if constexpr (TPF % 32 == 0) {
@@ -85,8 +96,15 @@ template <int N, int E, int TC> struct ColAddr {
     static constexpr bool kContiguous = false;
     // thread index = c + TC * t: the R_last adjacent t of all TC columns are R_last * TC consecutive threads
     static constexpr bool kLocalLast = plan_len(N, E) >= 2 && plan_radix(N, E, plan_len(N, E) - 1) * TC <= 32;
+    static constexpr bool kDualLayout = false;
+    static constexpr int kLow = 0xF;       // bits the column swizzles write (position space)
     int c;
     __device__ __forceinline__ int operator()(int p) const { return swz_col<N, E, TC>(p) * TC + c; }
+    template <int S, bool LOCAL> __device__ __forceinline__ int at(int t, int idx) const {
+        const int vt = swz_col<N, E, TC>(reg_pos<N, E, S>(t, 0));
+        const int k = swz_col<N, E, TC>(reg_pos<N, E, S>(0, idx));
+        return ((vt ^ (k & kLow)) * TC + c) + (k & ~kLow) * TC;
+    }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
@@ -128,8 +146,18 @@ template <typename T> struct RowArgs {
 };
 
 // One CTA = FPB rows, N/E threads per row.
+// Resident warps per SM the complex64 row pass is compiled for (register cap = 64 K / (32 * warps)): the pass overlaps the
+// shared-memory phases of some rows with the arithmetic of others only if enough independent rows are resident.
+#ifndef PA_ROW_MINWARPS
+#define PA_ROW_MINWARPS 0
+#endif
+template <typename T, int N, int E, int FPB> __host__ __device__ constexpr int row_min_blocks() {
+    constexpr int warps_per_cta = FPB * (N / E) / 32;
+    if (sizeof(T) != 4 || N < 2048 || warps_per_cta == 0 || PA_ROW_MINWARPS == 0) return 1;
+    return PA_ROW_MINWARPS / warps_per_cta > 0 ? PA_ROW_MINWARPS / warps_per_cta : 1;
+}
 template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC, bool MEAS = false>
-__global__ void __launch_bounds__(FPB * (N / E)) k_rows(RowArgs<T> a) {
+__global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>()) k_rows(RowArgs<T> a) {
     using C = cplx<T>;
     constexpr int TPF = N / E;
     extern __shared__ __align__(16) unsigned char smem_raw[];

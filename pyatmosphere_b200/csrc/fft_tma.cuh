@@ -53,10 +53,39 @@ template <typename T, int N, int E> struct TmaGeo {
     static constexpr int SLOT = TC * N * (int)sizeof(C);
     static constexpr int BOXR = N < 256 ? N : 256;                          // rows per tensor box
     static constexpr int SLOTS = ColSlots<N>::value;
-    static constexpr int SMEM = SLOTS * SLOT + 64;
     static constexpr bool OK = TC >= 1 && THREADS <= 1024 && THREADS >= 64 && TC * (int)sizeof(C) >= 16 && TC <= 32 &&
                                TmaRowGeo<T, N, E>::OK;
+    static constexpr int SMEM = SLOTS * SLOT + 64;
 };
+
+// Address map of the TMA-fed column kernel.  The tile arrives (and leaves) in the natural order [row][TC columns], and that
+// order is conflict-free for every exchange except the one between the last two stages (tools/bank_sim2.py).  So the
+// transform runs IN the delivered tile: exchanges between earlier stages use the natural order -- a thread's first exchange
+// writes exactly the addresses it read the tile from, its last exchange reads exactly the addresses it leaves its results
+// at -- and only the warp-local exchange between the last two stages moves to the swizzled order (swz_col), which stays
+// inside the block of 16 R_last rows that the same R_last adjacent threads own (kDualLayout; exchange() separates the two
+// layouts with a __syncwarp).  No copy between a "tile layout" and an "exchange layout", and none of their barriers.
+template <int N, int E, int TC> struct ColAddrDual {
+    static constexpr bool kContiguous = false;
+    static constexpr int L = plan_len(N, E);
+    static constexpr bool kLocalLast = L >= 2 && plan_radix(N, E, L - 1) * TC <= 32;
+    static constexpr bool kDualLayout = L >= 3 && kLocalLast;
+    static constexpr int kLow = 0xF;
+    // without the local layout the natural order must do for every exchange: true when a tile row fills a 128-byte bank row
+    static_assert(kDualLayout || TC * (E == 16 ? 8 : 16) >= 128, "TMA column tile: no conflict-free single layout");
+    int c;
+    template <int S, bool LOCAL> __device__ __forceinline__ int at(int t, int idx) const {
+        if constexpr (LOCAL && kDualLayout) {
+            const int vt = swz_col<N, E, TC>(reg_pos<N, E, S>(t, 0));
+            const int k = swz_col<N, E, TC>(reg_pos<N, E, S>(0, idx));
+            return ((vt ^ (k & kLow)) * TC + c) + (k & ~kLow) * TC;
+        } else {
+            return reg_pos<N, E, S>(t, 0) * TC + c + reg_pos<N, E, S>(0, idx) * TC;
+        }
+    }
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+
 
 template <typename T, int N, int E, bool IN_PERM, bool OUT_PERM>
 __global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArgs<T> a, int ntiles) {
@@ -134,21 +163,29 @@ __global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArg
     if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
 }
 
+// Column pass: persistent, one CTA per SM, tiles of TC adjacent columns travel through a ring of shared-memory slots
+// (TMA tensor loads in, TMA tensor stores out).  Per tile the compute threads meet at TWO block-wide barriers -- the two
+// exchanges that cross warps (first <-> second stage, forward and inverse); everything else is warp-local or an mbarrier the
+// warps arrive on without waiting: see ColAddrDual above.
 template <typename T, int N, int E>
-__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
+__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, TmaGeo<T, N, E>::THREADS <= 256 ? 2 : 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
     using C = cplx<T>;
     using G = TmaGeo<T, N, E>;
     constexpr int TC = G::TC, BOXR = G::BOXR, kColSlots = G::SLOTS;
     constexpr int kSlotBytes = G::SLOT;
-    const int TILES_PER_FIELD = a.ncols / TC;       // tiles per block of N rows
+    const int tiles_shift = 31 - __clz(a.ncols / TC);       // tiles per block of N rows (a power of two), as a shift
     constexpr int BOX_BYTES = BOXR * TC * (int)sizeof(C);
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     C* slots = reinterpret_cast<C*>(smem_tma);
     const uint32_t slot0 = ptx::smem_u32(smem_tma);
-    const uint32_t bar0 = slot0 + kColSlots * kSlotBytes;
+    const uint32_t full0 = slot0 + kColSlots * kSlotBytes;          // "tile has landed" (TMA transaction bytes)
+    const uint32_t done0 = full0 + 8 * kColSlots;                   // "every warp has left its results in the slot"
     const int c = threadIdx.x % TC, t = threadIdx.x / TC;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kColSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < kColSlots; ++s) {
+            ptx::mbar_init(full0 + 8 * s, 1);
+            ptx::mbar_init(done0 + 8 * s, G::THREADS / 32);
+        }
         ptx::fence_mbar_init();
     }
     __syncthreads();
@@ -156,32 +193,40 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) return;
         const int slot = k % kColSlots;
-        const int b = tile / TILES_PER_FIELD, col0 = (tile % TILES_PER_FIELD) * TC;
-        ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
+        const int b = tile >> tiles_shift, col0 = (tile & ((1 << tiles_shift) - 1)) * TC;
+        ptx::mbar_expect_tx(full0 + 8 * slot, kSlotBytes);
 #pragma unroll
         for (int r = 0; r < N / BOXR; ++r)
-            ptx::tma_load_2d(slot0 + slot * kSlotBytes + r * BOX_BYTES, &tmap, col0 * 2, b * N + r * BOXR, bar0 + 8 * slot);
+            ptx::tma_load_2d(slot0 + slot * kSlotBytes + r * BOX_BYTES, &tmap, col0 * 2, b * N + r * BOXR, full0 + 8 * slot);
+    };
+    auto issue_store = [&](int k) {
+        const int tile = blockIdx.x + k * gridDim.x;
+        const int slot = k % kColSlots;
+        const int b = tile >> tiles_shift, col0 = (tile & ((1 << tiles_shift) - 1)) * TC;
+        ptx::mbar_wait(done0 + 8 * slot, (k / kColSlots) & 1);
+#pragma unroll
+        for (int r = 0; r < N / BOXR; ++r) ptx::tma_store_2d(&tmap, col0 * 2, b * N + r * BOXR, slot0 + slot * kSlotBytes + r * BOX_BYTES);
+        ptx::bulk_commit();
     };
     if (threadIdx.x == 0) {
         issue_load(0);
         issue_load(1);
     }
-    const ColAddr<N, E, TC> addr{c};
+    const ColAddrDual<N, E, TC> addr{c};
     for (int k = 0;; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) break;
         const int slot = k % kColSlots;
         C* sm = slots + (size_t)slot * (kSlotBytes / sizeof(C));
-        const int col = (tile % TILES_PER_FIELD) * TC + c;
-        ptx::mbar_wait(bar0 + 8 * slot, (k / kColSlots) & 1);
+        const int col = (tile & ((1 << tiles_shift) - 1)) * TC + c;
+        ptx::mbar_wait(full0 + 8 * slot, (k / kColSlots) & 1);
         C v[E];
 #pragma unroll
-        for (int i = 0; i < E; ++i) v[i] = sm[reg_pos<N, E, 0>(t, i) * TC + c];
-        __syncthreads();
+        for (int i = 0; i < E; ++i) v[i] = sm[addr.template at<0, false>(t, i)];
         fft_fwd<T, N, E>(v, t, sm, addr, a.tw);
         {
             const C hx = cmul(ldg_c<T>(a.hp + col), mkc<T>(a.alpha_re, a.alpha_im));
-            const C* hy = a.hpy + ((tile / TILES_PER_FIELD) % a.nsub) * N;
+            const C* hy = a.hpy + ((tile >> tiles_shift) & (a.nsub - 1)) * N;
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 const C h = cmul(ldg_c<T>(hy + io_pos<N, E>(t, i)), hx);
@@ -189,27 +234,24 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, 1) k_cols_tma(const 
             }
         }
         if constexpr (kColSlots == 2) {
-            // two-slot ring: the other slot still holds tile k-1, whose store was committed at the end of the previous
-            // iteration and has long left shared memory by now; refill it with tile k+1 (half a tile time ahead of its use)
+            // two-slot ring: the other slot holds tile k-1, whose store was committed at the end of the previous iteration and
+            // has long left shared memory by now; refill it with tile k+1 (half a tile time ahead of its use)
             if (threadIdx.x == 0 && k >= 1) {
                 ptx::bulk_wait_read<0>();
                 issue_load(k + 1);
             }
         }
         fft_inv<T, N, E>(v, t, sm, addr, a.tw);
-        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < E; ++i) sm[reg_pos<N, E, 0>(t, i) * TC + c] = v[i];
-        ptx::fence_proxy_async();
-        __syncthreads();
+        for (int i = 0; i < E; ++i) sm[addr.template at<0, false>(t, i)] = v[i];
+        ptx::fence_proxy_async();                      // generic-proxy writes -> visible to the TMA store
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(done0 + 8 * slot);
         if (threadIdx.x == 0) {
-            const int b = tile / TILES_PER_FIELD, col0 = (tile % TILES_PER_FIELD) * TC;
-#pragma unroll
-            for (int r = 0; r < N / BOXR; ++r) ptx::tma_store_2d(&tmap, col0 * 2, b * N + r * BOXR, slot0 + slot * kSlotBytes + r * BOX_BYTES);
-            ptx::bulk_commit();
+            issue_store(k);
             if constexpr (kColSlots >= 3) {
-                ptx::bulk_wait_read<1>();
-                issue_load(k + 2);
+                ptx::bulk_wait_read<1>();                  // the store of tile k-1 has left its slot ...
+                issue_load(k + 2);                         // ... which is the slot of tile k+2
             }
         }
     }

@@ -216,7 +216,9 @@ def test_resumed_device_rng_run_draws_new_realizations(tmp_path):
     sim.run()
     data = np.asarray(again.measures[0].data)
     assert len(set(data.tolist())) == 10                                   # no duplicate samples
-    assert np.array_equal(data, np.asarray(full.measures[0].data))         # == the uninterrupted run
+    want = np.asarray(full.measures[0].data)
+    assert np.array_equal(data[6:], want[6:])                              # new draws == those of the uninterrupted run
+    assert np.allclose(data[:6], want[:6], rtol=1e-13, atol=0)             # (pandas' CSV float parser is not round-trip exact)
 
 
 def test_device_rng_uses_each_screens_own_ring_powers():
