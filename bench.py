@@ -332,6 +332,7 @@ def run_c3(args):
     table_d = torch.zeros((steps_total, B, stride), dtype=torch.float64, device=dev)
     stream = nat.stream_ptr()
     first = rank * steps_total * B          # disjoint global realization indices per rank
+    ps0 = ch.path.phase_screens[0]
 
     def step_device(i):
         nat.check(lib.pa_simulate_batch_device(h, desc.ref(), B, 1234, first + i * B, nat.ptr(edges_d), nat.ptr(psd_d),
@@ -352,80 +353,11 @@ def run_c3(args):
             d.td.all_reduce(sums)
         return hist, sums, tab
 
-    # ---- device-resident throughput ------------------------------------------------------------------------
-    # the clock sampler is started BEFORE the warm-up and given time to come up
-    sampler = ClockSampler(local)
-    if rank == 0 and not os.environ.get("PYATM_BENCH_NOSAMPLER"):
-        sampler.start()
-        time.sleep(0.2)
-    for i in range(args.warmup):
-        step_device(i)
-    reduce_stats(0, args.warmup)          # also warms up the lazily loaded torch / NCCL kernels of the reduction
-    d.barrier()
-    nat.launch_count(reset=True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    d.barrier()
-    t_begin = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        step_device(args.warmup + i)
-    hist, sums, tab = reduce_stats(args.warmup, steps_total)
-    e1.record()
-    d.barrier()
-    launches = nat.launch_count()
-    ms = d.max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
-    value = world * args.steps * B / (ms * 1e-3)
-    n_real = world * args.steps * B
-    mean_eta = float(sums[4].item()) / n_real
-    sem_eta = float(np.sqrt(max(float(sums[5].item()) / n_real - mean_eta**2, 0.0) / n_real))
-
-    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
-    ps0 = ch.path.phase_screens[0]
-    draws = HostDraws(torch, S, B, M, ps0.f_grid.base, ps0._get_psd(), seed=1000 + rank)
-    out_host = torch.zeros((B, stride), dtype=torch.float64).pin_memory()
-    pup_host = torch.from_numpy(pup).pin_memory()
-
-    def call_e2e(bufs):
-        fx, fy, cf = bufs
-        nat.check(lib.pa_simulate_batch(h, desc.ref(), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), 0, 0, None, None, nat.ptr(pup_host),
-                                        1, nat.ptr(out_host), stride, stream))
-
-    def e2e_loop(steps, live):
-        """`live`: every step's coefficients are drawn inside the timed region (host threads, up to 3 steps ahead);
-        otherwise four sets drawn beforehand are cycled (the host side a caller with its own generator would see)."""
-        if live:
-            for _ in range(min(3, steps)):
-                draws.submit()
-        d.barrier()
-        t0 = time.perf_counter()
-        for i in range(steps):
-            if live:
-                bufs = draws.next()
-                if i + 3 < steps:
-                    draws.submit()
-            else:
-                bufs = draws.sets[i % len(draws.sets)]
-            call_e2e(bufs)
-        d.barrier()
-        return d.max_over_ranks(time.perf_counter() - t0)
-
-    for k in range(len(draws.sets)):
-        draws._draw(k)
-    for i in range(max(1, min(args.warmup, 3))):
-        call_e2e(draws.sets[i % len(draws.sets)])
-    draws.draw_seconds = 0.0
-    dt_live = e2e_loop(args.steps, live=True)
-    draw_ms = 1e3 * draws.draw_seconds / args.steps
-    dt_pre = e2e_loop(args.steps, live=False)
-    draws.close()
-    e2e_value = world * args.steps * B / dt_live
-    h2d = 3 * S * B * M * 4 + S * B * M * 4 + pup.nbytes      # fx, fy (4 B) + coef (8 B) per ring + pupil table
-    d2h = B * stride * 8
-
-    roof = roof_screen = cpu = None
-    stats = {"hist_total": int(hist.sum().item()), "mean_eta": mean_eta, "sem_eta": sem_eta, "realizations": n_real}
-    if rank == 0:
+    def rooflines():
+        """Each pass / the screen synthesis timed ALONE with CUDA events on the launching stream, right after the warm-up
+        (burst conditions, like the copy that MEASURED_PEAKS.json's hbm_gbs comes from; inside the long timed loops the
+        board runs into its power cap -- see `clocks`)."""
+        roof = roof_screen = None
         # ---- roofline of the FFT passes (algorithmic bytes: 4 N^2 8 B per launch = half a split-step stage) -----
         Br = 8
         field = ctx.empty_field(Br)
@@ -487,6 +419,83 @@ def run_c3(args):
         except Exception as e:          # noqa: BLE001  (an extra, never fatal for the bench line)
             roof_screen = {"error": repr(e)}
         del field, turns
+        return roof, roof_screen
+
+    # ---- device-resident throughput ------------------------------------------------------------------------
+    # the clock sampler is started BEFORE the warm-up and given time to come up
+    sampler = ClockSampler(local)
+    if rank == 0 and not os.environ.get("PYATM_BENCH_NOSAMPLER"):
+        sampler.start()
+        time.sleep(0.2)
+    for i in range(args.warmup):
+        step_device(i)
+    reduce_stats(0, args.warmup)          # also warms up the lazily loaded torch / NCCL kernels of the reduction
+    d.barrier()
+    roof, roof_screen = rooflines() if rank == 0 else (None, None)
+    d.barrier()
+    nat.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d.barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_device(args.warmup + i)
+    hist, sums, tab = reduce_stats(args.warmup, steps_total)
+    e1.record()
+    d.barrier()
+    launches = nat.launch_count()
+    ms = d.max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop(t_begin, time.perf_counter()) if rank == 0 else None
+    value = world * args.steps * B / (ms * 1e-3)
+    n_real = world * args.steps * B
+    mean_eta = float(sums[4].item()) / n_real
+    sem_eta = float(np.sqrt(max(float(sums[5].item()) / n_real - mean_eta**2, 0.0) / n_real))
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------------
+    draws = HostDraws(torch, S, B, M, ps0.f_grid.base, ps0._get_psd(), seed=1000 + rank)
+    out_host = torch.zeros((B, stride), dtype=torch.float64).pin_memory()
+    pup_host = torch.from_numpy(pup).pin_memory()
+
+    def call_e2e(bufs):
+        fx, fy, cf = bufs
+        nat.check(lib.pa_simulate_batch(h, desc.ref(), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), 0, 0, None, None, nat.ptr(pup_host),
+                                        1, nat.ptr(out_host), stride, stream))
+
+    def e2e_loop(steps, live):
+        """`live`: every step's coefficients are drawn inside the timed region (host threads, up to 3 steps ahead);
+        otherwise four sets drawn beforehand are cycled (the host side a caller with its own generator would see)."""
+        if live:
+            for _ in range(min(3, steps)):
+                draws.submit()
+        d.barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            if live:
+                bufs = draws.next()
+                if i + 3 < steps:
+                    draws.submit()
+            else:
+                bufs = draws.sets[i % len(draws.sets)]
+            call_e2e(bufs)
+        d.barrier()
+        return d.max_over_ranks(time.perf_counter() - t0)
+
+    for k in range(len(draws.sets)):
+        draws._draw(k)
+    for i in range(max(1, min(args.warmup, 3))):
+        call_e2e(draws.sets[i % len(draws.sets)])
+    draws.draw_seconds = 0.0
+    dt_live = e2e_loop(args.steps, live=True)
+    draw_ms = 1e3 * draws.draw_seconds / args.steps
+    dt_pre = e2e_loop(args.steps, live=False)
+    draws.close()
+    e2e_value = world * args.steps * B / dt_live
+    h2d = 3 * S * B * M * 4 + S * B * M * 4 + pup.nbytes      # fx, fy (4 B) + coef (8 B) per ring + pupil table
+    d2h = B * stride * 8
+
+    cpu = None
+    stats = {"hist_total": int(hist.sum().item()), "mean_eta": mean_eta, "sem_eta": sem_eta, "realizations": n_real}
+    if rank == 0:
         # ---- CPU baseline: numpy port of the reference, one realization per seed on one core; the SAME seeds are then
         # replayed on the GPU from the same numpy draws and the transmittances compared (reference's complex64 floor)
         if not args.no_cpu:

@@ -234,7 +234,7 @@ template <int N, int E, int S> __device__ __forceinline__ int reg_pos(int t, int
 // ---- shared-memory exchange from the distribution of stage SA to that of stage SB --------------------------
 // A stage with SIGMA == 1 owns runs of R consecutive positions: with a contiguous address map (rows) and
 // complex64 data these are moved as 128-bit accesses (two elements), which is what the row swizzle is
-// conflict-free for (tools/bank_sim.py).
+// conflict-free for (tools/bank_sim2.py).
 // Addresses.  Every address map is  position -> (XOR swizzle that is GF(2)-linear in the bits of the position), and the
 // position of register idx of thread t splits into a thread part reg_pos(t, 0) and a register part reg_pos(0, idx) on
 // DISJOINT bits, so  addr(t, idx) = swz(thread part) ^ swz(register part)  with the second factor a compile-time constant

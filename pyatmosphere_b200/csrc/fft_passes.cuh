@@ -20,7 +20,7 @@ namespace pa {
 
 // ---- shared-memory address maps ----------------------------------------------------------------------------
 // XOR swizzles that keep runs aligned to their own size intact and spread the strided accesses of the
-// late stages over the banks (checked with tools/bank_sim.py).
+// late stages over the banks (checked with tools/bank_sim2.py).
 
 // Rows (complex64, E = 16; one 128-byte bank row = 16 elements).  Stage with SIGMA = 1: register pairs move as
 // 16-byte chunks, a quarter warp needs 8 distinct chunks -> thread bits enter chunk bits 1-3.  Stages with
@@ -148,13 +148,25 @@ template <typename T> struct RowArgs {
 // One CTA = FPB rows, N/E threads per row.
 // Resident warps per SM the complex64 row pass is compiled for (register cap = 64 K / (32 * warps)): the pass overlaps the
 // shared-memory phases of some rows with the arithmetic of others only if enough independent rows are resident.
+// Measured per size (tools/gpu/fft_variants.py, us per pass at 2048^2 x 8 / 4096^2 x 2 / 8192^2): 24 resident warps (80
+// registers) + screen values requested before the last inverse stage: 166 -> 131 / 168 -> 150; 8192^2 (one 512-thread CTA per
+// row) is best left alone (481 against 489); 32 warps (64 registers) spills: 171.
 #ifndef PA_ROW_MINWARPS
-#define PA_ROW_MINWARPS 0
+#define PA_ROW_MINWARPS 24
 #endif
+template <typename T, int N> struct RowTune {
+    static constexpr bool kTuned = sizeof(T) == 4 && (N == 2048 || N == 4096);
+    static constexpr int kMinWarps = kTuned ? PA_ROW_MINWARPS : 0;
+#ifdef PA_NO_PREFETCH_TURNS
+    static constexpr bool kPrefetchTurns = false;
+#else
+    static constexpr bool kPrefetchTurns = kTuned;    // request the screen values before the last inverse stage
+#endif
+};
 template <typename T, int N, int E, int FPB> __host__ __device__ constexpr int row_min_blocks() {
     constexpr int warps_per_cta = FPB * (N / E) / 32;
-    if (sizeof(T) != 4 || N < 2048 || warps_per_cta == 0 || PA_ROW_MINWARPS == 0) return 1;
-    return PA_ROW_MINWARPS / warps_per_cta > 0 ? PA_ROW_MINWARPS / warps_per_cta : 1;
+    if (warps_per_cta == 0 || RowTune<T, N>::kMinWarps == 0) return 1;
+    return RowTune<T, N>::kMinWarps / warps_per_cta > 0 ? RowTune<T, N>::kMinWarps / warps_per_cta : 1;
 }
 template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC, bool MEAS = false>
 __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>()) k_rows(RowArgs<T> a) {
@@ -168,9 +180,8 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
     C* ptr = a.field + (size_t)row * N;
     const RowAddr<N, E> addr{f * N};
     C v[E];
-#ifdef PA_PREFETCH_TURNS
-    T trv[E];
-#endif
+    constexpr bool PF = RowTune<T, N>::kPrefetchTurns && IN_PERM;
+    T trv[PF ? E : 1];
 
     if constexpr (SRC) {
       if (a.sep != nullptr) {
@@ -198,17 +209,17 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
     } else if constexpr (IN_PERM) {
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = ptr[io_pos<N, E>(t, i)];      // spectrum in storage order
-#ifdef PA_PREFETCH_TURNS
-        fft_inv_head<T, N, E>(v, t, sm, addr, a.tw);
-        if (a.turns != nullptr) {          // screen values requested before the last inverse stage hides their latency
-            const T* tr = a.turns + (size_t)row * N;
+        if constexpr (PF) {
+            fft_inv_head<T, N, E>(v, t, sm, addr, a.tw);
+            if (a.turns != nullptr) {          // screen values requested before the last inverse stage hides their latency
+                const T* tr = a.turns + (size_t)row * N;
 #pragma unroll
-            for (int i = 0; i < E; ++i) trv[i] = tr[reg_pos<N, E, 0>(t, i)];
+                for (int i = 0; i < E; ++i) trv[i] = tr[reg_pos<N, E, 0>(t, i)];
+            }
+            fft_inv_tail<T, N, E>(v, t, a.tw);
+        } else {
+            fft_inv<T, N, E>(v, t, sm, addr, a.tw);
         }
-        fft_inv_tail<T, N, E>(v, t, a.tw);
-#else
-        fft_inv<T, N, E>(v, t, sm, addr, a.tw);
-#endif
     } else {
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = ptr[reg_pos<N, E, 0>(t, i)];
@@ -219,11 +230,7 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
         const T* tr = a.turns + (size_t)row * N;
 #pragma unroll
         for (int i = 0; i < E; ++i) {
-#ifdef PA_PREFETCH_TURNS
-            C e = expm2pi(IN_PERM ? trv[i] : tr[reg_pos<N, E, 0>(t, i)]);
-#else
-            C e = expm2pi(tr[reg_pos<N, E, 0>(t, i)]);
-#endif
+            C e = expm2pi(PF ? trv[PF ? i : 0] : tr[reg_pos<N, E, 0>(t, i)]);
             e.x *= a.scale;
             e.y *= a.scale;
             v[i] = cmul(v[i], e);

@@ -188,73 +188,94 @@ template <bool PAIR> struct Ring {
 //                       Q: [screen][col block j/256][k block k/32]{hi,lo}[k chunk][col group (j%256)/8][j%8][k%8]
 // k = 2 r + {0,1} for ring rank r, where rank r is ring  m - 1 - r  (descending radius); ranks beyond the last
 // high ring are zero padding up to a multiple of 16 ranks (32 k).
-// One thread = one (row or column) x one k chunk of 8 = 4 rings.  grid: (n/128, kchunks, 2*nscreens), block 128.
+// grid: (n/128, 2*nscreens, KF_SPLIT), block 128; one thread = one row or column, 4 rings (one k chunk of 8) per step.
 // The phase argument coord * f is reduced mod 1 with an error-free float32 product (hi + lo), then the trigonometry
 // (MUFU) and the scaling run in float32: the operands only carry 22 bits (hi + lo).
-struct Split { __half hi, lo; };
-__device__ __forceinline__ Split split16(float v) {
-    Split s;
-    s.hi = __float2half_rn(v);
-    s.lo = __float2half_rn(v - __half2float(s.hi));
-    return s;
-}
+// One CTA = 128 rows (P) or columns (Q) of one screen x a range of K blocks: the ring frequencies and (pre-scaled)
+// coefficients of that range are staged in shared memory once, then every thread walks the K blocks with constant address
+// increments -- 4 rings (8 operand values, one 16-byte hi and one 16-byte lo store) per step.  (The first version spent 60 % of
+// its instructions on per-thread index arithmetic and ran at 2.6 TB/s of stores: 186 us for the 40 screens of a step.)
+constexpr int KF_SPLIT = 2;          // K range split over blockIdx.z: 2 x 16 x 80 = 2560 CTAs for a step of 8 realizations
 
 __global__ void __launch_bounds__(128) k_factors_tc(ScreenLaunch a, __half* P, __half* Q, int kpad, int pair) {
-    const int idx = blockIdx.x * 128 + threadIdx.x;           // row i (P) or column j (Q)
-    const int chunk = blockIdx.y;                              // k chunk of 8
-    const bool is_q = (blockIdx.z & 1) != 0;
-    const int s = blockIdx.z >> 1;
+    extern __shared__ __align__(16) unsigned char kf_smem[];
     const int nhigh = a.m - a.m_split;
-    const float coord = is_q ? __fadd_rn(a.x[idx], a.shift_x) : __fadd_rn(a.y[idx], a.shift_y);
+    const int nranks = kpad / 2;                               // ring ranks incl. zero padding
+    const int kblocks = kpad / BK;
+    const int kb_per = (kblocks + KF_SPLIT - 1) / KF_SPLIT;
+    const int kb0 = blockIdx.z * kb_per, kb1 = min(kblocks, kb0 + kb_per);
+    if (kb0 >= kb1) return;
+    const bool is_q = (blockIdx.y & 1) != 0;
+    const int s = blockIdx.y >> 1;
+    const int r0 = kb0 * (BK / 2), r1 = kb1 * (BK / 2);        // ranks [r0, r1)
+    float* sF = reinterpret_cast<float*>(kf_smem);             // [r1 - r0] frequency of rank r (0 for padding)
+    float2* sC = reinterpret_cast<float2*>(sF + (nranks + 3) / 4 * 4);   // [r1 - r0] coefficient * p_scale (P only)
     const float pscale = (float)a.p_scale;
-    __align__(16) __half hi[8];
-    __align__(16) __half lo[8];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int rank = chunk * 4 + q;
-        float v0 = 0.f, v1 = 0.f;
-        if (rank < nhigh) {
-            const int m = a.m - 1 - rank;
-            const size_t o = (size_t)s * a.m + m;
-            // coord * f mod 1 without float64: the product is hi + lo exactly (lo from one FMA), hi - rint(hi) is exact,
-            // and |lo| <= ulp(hi)/2 ~ 1.5e-5 turns, so the sum is good to 3e-8 turns like a rounded float64 result
-            const float f = is_q ? a.fx[o] : a.fy[o];
-            const float hi_t = __fmul_rn(coord, f);
-            const float lo_t = __fmaf_rn(coord, f, -hi_t);
-            const float turns = (hi_t - rintf(hi_t)) + lo_t;
-            // |angle| <= pi (+ 1e-4): the hardware approximations (abs. error ~4e-7 there) are as good as the 22-bit
-            // hi+lo operands, and four times cheaper than sincospif (this kernel is issue-bound)
-            const float ang = 6.283185307179586f * turns;
-            const float sn = __sinf(ang), cs = __cosf(ang);
-            if (is_q) {
-                v0 = cs * Q_SCALE;
-                v1 = sn * Q_SCALE;
-            } else {
-                const float2 c = a.coef[o];
-                v0 = (c.x * cs - c.y * sn) * pscale;
-                v1 = -(c.x * sn + c.y * cs) * pscale;
+    for (int r = r0 + threadIdx.x; r < r1; r += 128) {
+        float f = 0.f;
+        float2 c = make_float2(0.f, 0.f);
+        if (r < nhigh) {
+            const size_t o = (size_t)s * a.m + (a.m - 1 - r);  // rank r is ring m - 1 - r (descending radius)
+            f = is_q ? a.fx[o] : a.fy[o];
+            if (!is_q) {
+                c = a.coef[o];
+                c.x *= pscale;
+                c.y *= pscale;
             }
         }
-        const Split s0 = split16(v0), s1 = split16(v1);
-        hi[2 * q] = s0.hi; hi[2 * q + 1] = s1.hi;
-        lo[2 * q] = s0.lo; lo[2 * q + 1] = s1.lo;
+        sF[r - r0] = f;
+        if (!is_q) sC[r - r0] = c;
     }
+    __syncthreads();
+    const int idx = blockIdx.x * 128 + threadIdx.x;            // row i (P) or column j (Q)
+    const float coord = is_q ? __fadd_rn(a.x[idx], a.shift_x) : __fadd_rn(a.y[idx], a.shift_y);
     const int tile = is_q ? TN : TM;
     const int half_bytes = is_q ? Q_HALF : P_HALF;
-    const int nblk = a.n / tile;
     const int blk = idx / tile, within = idx % tile;
-    const int kb = chunk / 4, kc = chunk % 4;
-    __half* base = is_q ? Q : P;
     // within one hi / lo block: [k chunk][col or row group][8][8]; for CTA pairs the Q block is stored as two contiguous
     // halves of 128 columns (one per CTA of the pair), each [k chunk][16 col groups][8][8]
-    size_t inner = (size_t)kc * (tile / 8) * 128 + (size_t)(within / 8) * 128 + (within % 8) * 16;
+    size_t inner = (size_t)(within / 8) * 128 + (within % 8) * 16;
+    int kc_stride = (tile / 8) * 128;
     if (is_q && pair) {
         const int cg = within / 8;
-        inner = (size_t)(cg / 16) * (half_bytes / 2) + (size_t)kc * 16 * 128 + (size_t)(cg % 16) * 128 + (within % 8) * 16;
+        inner = (size_t)(cg / 16) * (half_bytes / 2) + (size_t)(cg % 16) * 128 + (within % 8) * 16;
+        kc_stride = 16 * 128;
     }
-    char* dst = (char*)base + (((size_t)s * nblk + blk) * (kpad / BK) + kb) * (size_t)(2 * half_bytes) + inner;
-    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
-    *reinterpret_cast<uint4*>(dst + half_bytes) = *reinterpret_cast<const uint4*>(lo);
+    char* dst = (char*)(is_q ? Q : P) + (((size_t)s * (a.n / tile) + blk) * kblocks + kb0) * (size_t)(2 * half_bytes) + inner;
+    for (int kb = kb0; kb < kb1; ++kb, dst += 2 * half_bytes) {
+#pragma unroll
+        for (int kc = 0; kc < BK / 8; ++kc) {
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int r = (kb - kb0) * (BK / 2) + kc * 4 + q;
+                // coord * f mod 1 without float64: the product is hi + lo exactly (lo from one FMA), hi - rint(hi) is exact,
+                // and |lo| <= ulp(hi)/2 ~ 1.5e-5 turns, so the sum is good to 3e-8 turns like a rounded float64 result
+                const float f = sF[r];
+                const float hi_t = __fmul_rn(coord, f);
+                const float lo_t = __fmaf_rn(coord, f, -hi_t);
+                const float turns = (hi_t - rintf(hi_t)) + lo_t;
+                // |angle| <= pi (+ 1e-4): the hardware approximations (abs. error ~4e-7 there) are as good as the 22-bit
+                // hi+lo operands
+                const float ang = 6.283185307179586f * turns;
+                const float sn = __sinf(ang), cs = __cosf(ang);
+                float v0, v1;
+                if (is_q) {
+                    v0 = cs * Q_SCALE;
+                    v1 = sn * Q_SCALE;
+                } else {
+                    const float2 c = sC[r];
+                    v0 = c.x * cs - c.y * sn;
+                    v1 = -(c.x * sn + c.y * cs);
+                }
+                hi[q] = __floats2half2_rn(v0, v1);
+                const float2 back = __half22float2(hi[q]);
+                lo[q] = __floats2half2_rn(v0 - back.x, v1 - back.y);
+            }
+            *reinterpret_cast<uint4*>(dst + kc * kc_stride) = *reinterpret_cast<const uint4*>(hi);
+            *reinterpret_cast<uint4*>(dst + kc * kc_stride + half_bytes) = *reinterpret_cast<const uint4*>(lo);
+        }
+    }
 }
 
 // ---- low-ring polynomial at the interpolation nodes --------------------------------------------------------------
@@ -757,8 +778,9 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     // (cp.async.bulk.tensor ... cta_group::2), which needs the operands behind tensor maps.
     static const bool pair = !(getenv("PYATM_TC_PAIR") && atoi(getenv("PYATM_TC_PAIR")) == 0) && !(swap & 128);
     if (phase == 0 || phase == 2) {
-        dim3 gf(a.n / 128, kpad / 8, 2 * a.nscreens);
-        k_factors_tc<<<gf, 128, 0, st>>>(a, P, Q, kpad, pair ? 1 : 0);
+        dim3 gf(a.n / 128, 2 * a.nscreens, KF_SPLIT);
+        const size_t kf_smem = ((size_t)(kpad / 2 + 3) / 4 * 4) * sizeof(float) + (size_t)(kpad / 2) * sizeof(float2);
+        k_factors_tc<<<gf, 128, kf_smem, st>>>(a, P, Q, kpad, pair ? 1 : 0);
         if (a.degree >= 0) {
             dim3 gu((nq + 127) / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride, nq);

@@ -25,7 +25,7 @@ def main(path):
     usual = max(set(lengths), key=lengths.count)
     a0, b0 = [sp for sp, ln in zip(spans, lengths) if ln == usual][-1]
     step = rows[a0:b0]
-    step = [(k, t) for k, t in step if "pa::" in k or "tc::" in k]
+    step = [(k, t) for k, t in step if "k_" in k]       # this library's kernels (ncu prints some without their namespace)
     total = sum(t for _, t in step)
     agg = OrderedDict()
     for k, t in step:
