@@ -22,9 +22,11 @@
 // launch each per batch of screens) and stored as float32 triples (hi, lo, node value in turns).
 // Operands are pre-tiled in global memory by k_factors_tc in the canonical K-major / no-swizzle UMMA layout
 // (8 rows x 16 bytes core matrices), so one bulk copy per operand and stage fills shared memory.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 #include "internal_screen.h"
@@ -127,6 +129,15 @@ __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, u
         "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+// Operand tile through a tensor map, issued by either CTA of a pair: the bytes land in the issuing CTA's shared memory, the
+// transaction count is credited to the LEADER's mbarrier (peer bit of the shared::cluster address cleared), so the leader's
+// "full" barrier sees the operands of both CTAs without any relay thread.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma2d_pair(uint32_t dst, const void* tmap, int x, int y, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(tmap), "r"(bar & kPeerBitMask), "r"(x), "r"(y)
+                 : "memory");
 }
 // completion of all earlier MMAs of the pair -> one arrival on the mbarrier at this offset in BOTH CTAs
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
@@ -388,6 +399,10 @@ __device__ constexpr float kLag[16][6] = {
 
 // ---- contraction + epilogue ---------------------------------------------------------------------------------
 struct TcArgs {
+    // operand buffers as 2-D tensors of fp16: rows of 256 halves (512 bytes); one box = 16 rows = 8 KiB (pair kernel, TMAP mode)
+    alignas(64) CUtensorMap mapP;
+    alignas(64) CUtensorMap mapQ;
+    int use_tmap;
     ScreenLaunch a;
     const __half* P;
     const __half* Q;
@@ -411,7 +426,7 @@ struct TcArgs {
 // bulk copies alone 67 us, both together 105 us).  The leader CTA (cluster rank 0) issues the MMAs for both; the peer's
 // MMA warp only relays "my operands have landed".
 template <bool PAIR>
-__global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
+__global__ void __launch_bounds__(THREADS, 1) k_screen_tc(const __grid_constant__ TcArgs g) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const ScreenLaunch& a = g.a;
     using R = Ring<PAIR>;
@@ -493,13 +508,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                         continue;
                     }
-                    mbar_expect_tx(full_bar(stage), (uint32_t)nsub * R::KB_BYTES);
+                    const bool tmap = PAIR && g.use_tmap;
+                    // tensor-map mode: the leader's barrier collects the bytes of both CTAs; the peer only issues its copies
+                    if (!tmap) mbar_expect_tx(full_bar(stage), (uint32_t)nsub * R::KB_BYTES);
+                    else if (rank == 0) mbar_expect_tx(full_bar(stage), 2u * (uint32_t)nsub * R::KB_BYTES);
                     constexpr int CH = 8192;      // several 8 KiB copies in flight instead of two large ones
 #pragma unroll
                     for (int sub = 0; sub < R::SUB; ++sub) {
                         if (R::SUB > 1 && sub >= nsub) break;
                         const int kb = kb0 + sub;
                         const uint32_t dst = smem_u32(stage_base + (size_t)stage * STAGE_BYTES + (size_t)sub * R::KB_BYTES);
+                        if (tmap) {
+                            // the same 8 KiB pieces as below, addressed as 16-row boxes of the operand tensors
+                            const size_t prow = (size_t)(psrc - (const char*)g.P + (size_t)kb * P_STAGE) / 512;
+                            const size_t qrow = (size_t)(qsrc - (const char*)g.Q + (size_t)kb * Q_STAGE + rank * R::Q_HALF_BYTES) / 512;
+#pragma unroll
+                            for (int o = 0; o < P_STAGE; o += CH) tma2d_pair(dst + o, &g.mapP, 0, (int)(prow + o / 512), full_bar(stage));
+#pragma unroll
+                            for (int hl = 0; hl < 2; ++hl)
+                                tma2d_pair(dst + P_STAGE + hl * R::Q_HALF_BYTES, &g.mapQ, 0, (int)(qrow + (size_t)hl * Q_HALF / 512), full_bar(stage));
+                            continue;
+                        }
 #pragma unroll
                         for (int o = 0; o < P_STAGE; o += CH) bulk_g2s(dst + o, psrc + (size_t)kb * P_STAGE + o, CH, full_bar(stage));
                         if constexpr (PAIR) {
@@ -521,7 +550,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
         // ===== MMA issuer =====
         if (PAIR && rank != 0) {
             // ===== peer CTA: no MMAs of its own -- tell the leader when this CTA's operands of a stage have landed =====
-            if (lane == 0) {
+            if (lane == 0 && !g.use_tmap) {
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int tile = first_tile; tile < g.total_tiles; tile += tile_step) {
@@ -551,7 +580,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_screen_tc(TcArgs g) {
                     const int nsub = g.kblocks - kb0 < R::SUB ? g.kblocks - kb0 : R::SUB;
                     mbar_wait(full_bar(stage), phase, g.err);
                     if constexpr (PAIR)
-                        if (!(g.swap_lbo_sbo & 16)) mbar_poll(peerfull_bar(stage), phase, g.err);      // bit 16: timing experiment without the relay
+                        if (!(g.swap_lbo_sbo & 16) && !g.use_tmap) mbar_poll(peerfull_bar(stage), phase, g.err);   // bit 16: timing experiment without the relay
                     tc_fence_after();
 #pragma unroll
                   for (int sub = 0; sub < R::SUB; ++sub) {
@@ -796,6 +825,38 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     if (pair)
         if (cudaError_t e = attr_done_pair.raise(k_screen_tc<true>, SMEM_BYTES_PAIR); e != cudaSuccess) return (int)e;
     TcArgs g;
+    memset(&g.mapP, 0, sizeof(g.mapP));
+    memset(&g.mapQ, 0, sizeof(g.mapQ));
+    // UNVERIFIED ON HARDWARE (written after the round's GPU budget was spent): PYATM_TC_PAIR_TMAP=1 loads the operands of
+    // the pair kernel through tensor maps with cta_group::2 so that the peer's bytes are credited to the leader's barrier
+    // (no relay thread).  Off by default until tests/test_gpu_screen_tc.py has been run with it.
+    static const bool want_tmap = getenv("PYATM_TC_PAIR_TMAP") && atoi(getenv("PYATM_TC_PAIR_TMAP")) != 0;
+    g.use_tmap = 0;
+    if (pair && want_tmap) {
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        static EncodeFn encode = nullptr;
+        if (!encode) {
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+                return (int)cudaErrorNotSupported;
+            encode = (EncodeFn)fn;
+        }
+        const size_t bytes = (size_t)a.nscreens * pq_stride * sizeof(__half);       // per operand, this launch's screens
+        const cuuint64_t dims[2] = {256, (cuuint64_t)(bytes / 512)};
+        const cuuint64_t strides[1] = {512};
+        const cuuint32_t box[2] = {256, 16};
+        const cuuint32_t estr[2] = {1, 1};
+        for (int w = 0; w < 2; ++w) {
+            const CUresult r = encode(w ? &g.mapQ : &g.mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w ? (void*)Q : (void*)P, dims, strides, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return (int)cudaErrorInvalidValue;
+        }
+        g.use_tmap = 1;
+    }
     g.a = a;
     g.P = P;
     g.Q = Q;
