@@ -162,6 +162,24 @@ PA_API int pa_simulate_batch_device(pa_ctx* ctx, const pa_path* path, int batch,
 PA_API int pa_fft_pass(pa_ctx* ctx, void* field_dev, int batch, int kind, const void* turns_dev, double length,
                        double wvl, void* stream);
 
+/* ---- the one collective of the path ----------------------------------------------------------------------------
+ * Independent realizations are sharded over the GPUs; what the reference computes from one process's
+ * samples -- the 200-bin transmittance histograms (simulations/pdt.py:30-31) and the sums behind sigma_BW / sigma_LT / W_ST
+ * (simulations/beam.py:35-71) -- is summed over the ranks here, on the device, over NCCL (NVLink / NVSwitch).  NCCL is bound
+ * with dlopen("libnccl.so.2") at the first call (override: PYATM_NCCL_LIB); hosts that never create a pa_comm never need it.
+ * The 128-byte id is created on one rank and handed to the others by the host (any side channel: file, MPI, sockets,
+ * torch.distributed's object broadcast); id_out / id point to PA_COMM_ID_BYTES bytes. */
+#define PA_COMM_ID_BYTES 128
+typedef struct pa_comm pa_comm;
+PA_API int pa_comm_unique_id(unsigned char* id_out);
+PA_API int pa_comm_create(pa_comm** comm, int device, int rank, int world, const unsigned char* id);
+PA_API int pa_comm_destroy(pa_comm* comm);
+/* Sum over the ranks of what simulations/pdt.py:30-31 (histogram counts) and simulations/beam.py:35-71 (n, sum v, sum v^2)
+ * accumulate per process.  In place, both buffers on the device of the communicator: hist_dev [nbins] uint64 counts
+ * (pa_histogram), sums_dev [nsums] float64; either count may be 0.  Asynchronous on `stream`. */
+PA_API int pa_stats_allreduce(pa_comm* comm, unsigned long long* hist_dev, size_t nbins, double* sums_dev, size_t nsums,
+                              void* stream);
+
 /* number of kernel launches issued by this library since the counter was last reset (bench.py gpu_launches) */
 PA_API unsigned long long pa_launch_count(int reset);
 

@@ -57,7 +57,12 @@ SIGNATURES = {
                                  _int, _vp]),
     "pa_simulate_batch_device": (_int, [_vp, C.POINTER(PaPath), _int, _u64, _u64, _vp, _vp, _vp, _int, _vp, _int,
                                         _vp]),
+    "pa_comm_unique_id": (_int, [_vp]),
+    "pa_comm_create": (_int, [C.POINTER(_vp), _int, _int, _int, _vp]),
+    "pa_comm_destroy": (_int, [_vp]),
+    "pa_stats_allreduce": (_int, [_vp, _vp, _sz, _vp, _sz, _vp]),
 }
+COMM_ID_BYTES = 128
 
 _lib = None
 _lock = threading.Lock()

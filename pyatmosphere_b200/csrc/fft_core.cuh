@@ -22,6 +22,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef PA_E32
+#define PA_E32 16       // complex64 elements per thread (internal.h); 8 is an experiment switch
+#endif
+
 namespace pa {
 
 // ---- radix plan (compile time) ------------------------------------------------------------------------

@@ -50,7 +50,7 @@ template <int N, int E> __device__ __forceinline__ int swz_row(int p) {
 // R_last -> those bits are folded onto the low bits.  Every other stage is conflict-free in the natural order.
 template <int N, int E, int TC> __device__ __forceinline__ int swz_col(int p) {
     constexpr int RL = plan_radix(N, E, plan_len(N, E) - 1);
-    constexpr int SLOTS = E == 16 ? 4 : 3;          // log2 of the elements per 128-byte bank row
+    constexpr int SLOTS = (E == 16 || PA_E32 == 8) ? 4 : 3;          // log2 of the elements per 128-byte bank row (PA_E32 == 8: experiment)
     constexpr int W = ilog2(TC) >= SLOTS ? 0 : SLOTS - ilog2(TC);
     if constexpr (W == 0) {
         return p;
@@ -168,7 +168,8 @@ template <typename T, int N, int E, int FPB> __host__ __device__ constexpr int r
     if (warps_per_cta == 0 || RowTune<T, N>::kMinWarps == 0) return 1;
     return RowTune<T, N>::kMinWarps / warps_per_cta > 0 ? RowTune<T, N>::kMinWarps / warps_per_cta : 1;
 }
-template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC, bool MEAS = false>
+// MEAS: 0 = plain pass; 1 + NP = final pass with the reductions fused in, NP apertures (0..kFusedPupils) compiled in
+template <typename T, int N, int E, int FPB, bool IN_PERM, bool OUT_PERM, bool SRC, int MEAS = 0>
 __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>()) k_rows(RowArgs<T> a) {
     using C = cplx<T>;
     constexpr int TPF = N / E;
@@ -248,24 +249,25 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
 #pragma unroll
         for (int i = 0; i < E; ++i) ptr[io_pos<N, E>(t, i)] = v[i];
     } else {
-        if (!MEAS || a.store) {
+        if (MEAS == 0 || a.store) {
 #pragma unroll
             for (int i = 0; i < E; ++i) ptr[reg_pos<N, E, 0>(t, i)] = v[i];
         }
-        if constexpr (MEAS) {
+        if constexpr (MEAS != 0) {
             // same arithmetic as k_measure_partial (measure.cu): intensity and x-weights in the field's precision,
             // aperture predicate in float32 without FMA contraction (pupils.py:10)
+            constexpr int NP = MEAS - 1;                           // apertures reduced here
+            constexpr int NS = 3 + NP;                             // live sums
             const float yv = a.y[row % N];
-            float pr2[kFusedPupils], psx[kFusedPupils], dy2[kFusedPupils];
-            T acc[kRowSums];
+            float pr2[NP > 0 ? NP : 1], psx[NP > 0 ? NP : 1], dy2[NP > 0 ? NP : 1];
+            T acc[NS];
 #pragma unroll
-            for (int q = 0; q < kRowSums; ++q) acc[q] = 0;
+            for (int q = 0; q < NS; ++q) acc[q] = 0;
 #pragma unroll
-            for (int p = 0; p < kFusedPupils; ++p) {
-                const bool on = p < a.npupil;
-                pr2[p] = on ? a.pupils[3 * p] : -1.0f;
-                psx[p] = on ? a.pupils[3 * p + 1] : 0.0f;
-                const float dy = __fadd_rn(yv, on ? a.pupils[3 * p + 2] : 0.0f);
+            for (int p = 0; p < NP; ++p) {
+                pr2[p] = a.pupils[3 * p];
+                psx[p] = a.pupils[3 * p + 1];
+                const float dy = __fadd_rn(yv, a.pupils[3 * p + 2]);
                 dy2[p] = __fmul_rn(dy, dy);
             }
 #pragma unroll
@@ -276,15 +278,15 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
                 acc[1] += in * (T)xv;
                 acc[2] += in * ((T)xv * (T)xv);
 #pragma unroll
-                for (int p = 0; p < kFusedPupils; ++p) {
+                for (int p = 0; p < NP; ++p) {
                     const float dx = __fsub_rn(xv, psx[p]);
                     acc[3 + p] += (__fadd_rn(__fmul_rn(dx, dx), dy2[p]) <= pr2[p]) ? in : (T)0;
                 }
             }
             // reduce over the N/E threads of the row: shuffles, then one slot per warp in shared memory
-            double red[kRowSums];
+            double red[NS];
 #pragma unroll
-            for (int q = 0; q < kRowSums; ++q) {
+            for (int q = 0; q < NS; ++q) {
                 double r = (double)acc[q];
                 for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
                 red[q] = r;
@@ -294,12 +296,13 @@ __global__ void __launch_bounds__(FPB * (N / E), row_min_blocks<T, N, E, FPB>())
             double* sred = reinterpret_cast<double*>(smem_raw) + (size_t)f * (N * sizeof(C) / sizeof(double));
             if ((t & 31) == 0) {
 #pragma unroll
-                for (int q = 0; q < kRowSums; ++q) sred[(t >> 5) * kRowSums + q] = red[q];
+                for (int q = 0; q < NS; ++q) sred[(t >> 5) * kRowSums + q] = red[q];
             }
             __syncthreads();
             if (t < kRowSums) {
                 double r = 0.0;
-                for (int w = 0; w < WPR; ++w) r += sred[w * kRowSums + t];
+                if (t < NS)
+                    for (int w = 0; w < WPR; ++w) r += sred[w * kRowSums + t];
                 a.rowsums[(size_t)row * kRowSums + t] = r;
             }
         }

@@ -72,7 +72,7 @@ template <int N, int E, int TC> struct ColAddrDual {
     static constexpr bool kDualLayout = L >= 3 && kLocalLast;
     static constexpr int kLow = 0xF;
     // without the local layout the natural order must do for every exchange: true when a tile row fills a 128-byte bank row
-    static_assert(kDualLayout || TC * (E == 16 ? 8 : 16) >= 128, "TMA column tile: no conflict-free single layout");
+    static_assert(kDualLayout || TC * (E == 16 ? 8 : 16) >= 128 || PA_E32 == 8, "TMA column tile: no conflict-free single layout");
     int c;
     template <int S, bool LOCAL> __device__ __forceinline__ int at(int t, int idx) const {
         if constexpr (LOCAL && kDualLayout) {

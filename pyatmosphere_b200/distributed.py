@@ -120,3 +120,53 @@ def reduce_statistics(local_table: np.ndarray, columns: dict, eta_names=(), bins
         h = np.histogram(t[:, columns[name]], bins=bins, range=(0, 1))[0].astype(np.int64)
         out[("hist", name)] = allreduce_sum(h)
     return out
+
+
+class StatsComm:
+    """The collective of the path behind the C ABI (pa_comm_* / pa_stats_allreduce, include/pyatm_b200.h): an NCCL communicator
+    owned by libpyatm_b200.so.  The 128-byte id is made on rank 0 and reaches the other ranks through whatever side channel
+    the host has -- here torch.distributed's object broadcast when a process group is up, or the `unique_id` argument.
+
+        comm = StatsComm()                       # under torchrun, after init_process_group
+        comm.allreduce(hist_dev, sums_dev)       # in place, on the current stream
+    """
+
+    def __init__(self, rank=None, world=None, unique_id=None, device=None):
+        import ctypes as C
+        from . import _native as nat
+        torch = nat.torch_mod()
+        lib = nat.load()
+        w, r = world_rank()
+        self.rank = r if rank is None else int(rank)
+        self.world = w if world is None else int(world)
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        if unique_id is None:
+            buf = (C.c_ubyte * nat.COMM_ID_BYTES)()
+            if self.rank == 0:
+                nat.check(lib.pa_comm_unique_id(C.cast(buf, C.c_void_p)))
+            box = [bytes(buf)]
+            if self.world > 1:
+                _td().broadcast_object_list(box, src=0)
+            unique_id = box[0]
+        self.unique_id = bytes(unique_id)
+        idbuf = (C.c_ubyte * nat.COMM_ID_BYTES).from_buffer_copy(self.unique_id)
+        self.handle = C.c_void_p()
+        nat.check(lib.pa_comm_create(C.byref(self.handle), self.device, self.rank, self.world, C.cast(idbuf, C.c_void_p)))
+        self.lib = lib
+
+    def allreduce(self, hist_dev=None, sums_dev=None):
+        """Sum a uint64/int64 histogram tensor and a float64 vector over the ranks, in place, on the current stream."""
+        from . import _native as nat
+        nat.check(self.lib.pa_stats_allreduce(self.handle, nat.ptr(hist_dev), 0 if hist_dev is None else hist_dev.numel(),
+                                              nat.ptr(sums_dev), 0 if sums_dev is None else sums_dev.numel(), nat.stream_ptr()))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.pa_comm_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:       # noqa: BLE001
+            pass

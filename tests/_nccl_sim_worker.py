@@ -28,6 +28,18 @@ t = torch.as_tensor(np.concatenate([table.ravel(), etas]), device="cuda")
 ref = t.clone()
 td.broadcast(ref, src=0)
 assert torch.equal(t, ref), "ranks disagree"
+# the collective behind the C ABI (pa_comm_* / pa_stats_allreduce): histogram + sums over the ranks == torch's all-reduce
+from pyatmosphere_b200.distributed import StatsComm  # noqa: E402
+comm = StatsComm()
+hist = torch.arange(200, dtype=torch.int64, device="cuda") * (rank + 1)
+sums = torch.tensor([1.5, -2.0, 1e-9], dtype=torch.float64, device="cuda") * (rank + 1)
+want_h, want_s = hist.clone(), sums.clone()
+td.all_reduce(want_h)
+td.all_reduce(want_s)
+comm.allreduce(hist, sums)
+torch.cuda.synchronize()
+assert torch.equal(hist, want_h) and torch.allclose(sums, want_s, rtol=1e-15, atol=0), "pa_stats_allreduce differs from torch.distributed"
+comm.close()
 if rank == 0:
     np.save(os.environ.get("PYATM_NCCL_OUT", "/tmp/nccl_records.npy"), np.concatenate([table.ravel(), etas]))
 td.barrier()

@@ -254,3 +254,20 @@ def test_device_rng_uses_each_screens_own_ring_powers():
     nat.check(ctx.lib.pa_propagate(ctx.handle, desc.ref(), nat.ptr(field), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), nat.stream_ptr()))
     etas = [pa.measures.eta(ch, output=ch.pupil.output(pa.gpu.DeviceArray(field[i]))) for i in range(B)]
     assert np.allclose(pdt.measures[0].data, etas, rtol=1e-6)
+
+
+def test_stats_allreduce_behind_the_c_abi_single_rank():
+    """pa_comm_* / pa_stats_allreduce (NCCL bound with dlopen inside libpyatm_b200.so): a one-rank communicator reduces in
+    place to the same values; either buffer may be absent.  (Two ranks: tests/_nccl_sim_worker.py on a two-GPU box.)"""
+    import torch
+    from pyatmosphere_b200.distributed import StatsComm
+    comm = StatsComm(rank=0, world=1)
+    hist = torch.arange(200, dtype=torch.int64, device="cuda")
+    sums = torch.tensor([0.25, -3.0], dtype=torch.float64, device="cuda")
+    comm.allreduce(hist, sums)
+    comm.allreduce(hist, None)
+    comm.allreduce(None, sums)
+    torch.cuda.synchronize()
+    assert torch.equal(hist.cpu(), torch.arange(200, dtype=torch.int64)) and sums.cpu().tolist() == [0.25, -3.0]
+    assert len(comm.unique_id) == 128
+    comm.close()

@@ -305,7 +305,8 @@ def test_header_cites_the_reference_for_every_compute_entry_point():
     replaces in the comment block in front of it (utility entry points -- version, error text, counters, profiling -- excepted)."""
     hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
     utilities = {"pa_version", "pa_last_error", "pa_device_count", "pa_launch_count", "pa_ctx_destroy", "pa_ctx_permutation",
-                 "pa_ctx_fft_geometry", "pa_fft_pass", "pa_phase_to_turns", "pa_simulate_batch_device"}
+                 "pa_ctx_fft_geometry", "pa_fft_pass", "pa_phase_to_turns", "pa_simulate_batch_device", "pa_comm_unique_id",
+                 "pa_comm_create", "pa_comm_destroy"}
     cite = re.compile(r"[\w/]+\.py:\d+")
     last_comment = ""
     checked = 0
@@ -327,7 +328,7 @@ def test_c_abi_rejects_null_arguments_with_a_status_code():
     for name, (_, args) in nat.SIGNATURES.items():
         if name in skip:
             continue
-        call = [0.0 if a is C.c_double else (None if a in (C.c_void_p, C.POINTER(nat.PaPath)) else 0) for a in args]
+        call = [0.0 if a is C.c_double else (None if a in (C.c_void_p, C.POINTER(nat.PaPath), C.POINTER(C.c_void_p)) else 0) for a in args]
         assert getattr(lib, name)(*call) == 1, name
         assert b"bad arguments" in lib.pa_last_error(), name
     assert lib.pa_ctx_destroy(None) == 0                      # destroying nothing is not an error
