@@ -5,7 +5,7 @@
 Workloads (BASELINE.json configs):
   c3 (default, the configuration the metric is quoted on): a step is one batch of B = 160 independent realizations of the
      whole hot path (device RNG -> 5 x [leg + screen synthesis + screen multiply] -> closing leg -> fused measures), one
-     pa_simulate_batch_device call.  `e2e` is the same batch through pa_simulate_batch with HOST coefficient buffers
+     pa_simulate_batch_device call (the library works through it in chunks of 32).  `e2e` is the same batch through pa_simulate_batch with HOST coefficient buffers
      (drawn on host threads inside the timed region), copies in and table out.
   c4: Simulation([BeamResult, PDTResult]).run() -- the call a user of the reference makes -- for 6000 device-RNG
      realizations of the same channel, sharded over the ranks, one all-gather of the records at the end.
@@ -37,6 +37,10 @@ WORKLOAD = "README advanced channel: 2048^2 grid, delta 1.5 mm, 5 SS screens (MV
 WORKLOAD_C5 = "long-haul stress: 8192^2 grid, delta 0.75 mm, 20 SS screens (MVK, 2^10 rings), 100 km"
 METRIC = "channel realizations/sec (2048^2, 5 screens)"
 UNIT = "realizations/s"
+# identical in the b200 and the reference arm (the driver compares the two `config` objects); per-arm details go to `run`
+CONFIG = {"workload": WORKLOAD,
+          "l2": "inputs larger than L2: one realization sweeps a 32 MiB field and five 16 MiB screens through six legs; the "
+                "GPU arm works on chunks of 32 realizations (1.5 GiB against 126 MB of L2)"}
 
 
 def measured_peaks():
@@ -150,7 +154,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "complex64 (numpy: c128 transfer-function product, as the reference)", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "realizations_per_step": workers},
+        "config": CONFIG, "run": {"realizations_per_step": workers, "worker_processes": workers},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -428,7 +432,9 @@ def run_c3(args):
     if rank == 0 and not os.environ.get("PYATM_BENCH_NOSAMPLER"):
         sampler.start()
         time.sleep(0.2)
-    step_device(0)                        # contexts, tables and workspaces exist; then the pass rooflines, before any long load
+    # the pass rooflines first, on an idle board at its boost clocks: a kernel timed alone (7 ms of launches), like the copy
+    # behind MEASURED_PEAKS.json; the long loops below run into the power cap (see `clocks`)
+    time.sleep(0.3)
     roof, roof_screen = rooflines() if rank == 0 else (None, None)
     d.barrier()
     for i in range(args.warmup):
@@ -529,9 +535,9 @@ def run_c3(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "realizations_per_step_per_gpu": B, "screen_method": args.screen_method,
-                       "rng": "device Philox4x32-10 (value) / host-drawn coefficients in pinned memory (e2e)",
-                       "l2": "inputs larger than L2: every chunk of 8 realizations sweeps 384 MiB of field + screen (126 MB L2)"},
+            "config": CONFIG,
+            "run": {"realizations_per_step_per_gpu": B, "screen_method": args.screen_method,
+                    "rng": "device Philox4x32-10 (value) / host-drawn coefficients in pinned memory (e2e)"},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "api": "pa_simulate_batch (C ABI, host buffers in, per-realization table out), coefficients drawn on 3 host "

@@ -144,7 +144,7 @@ PA_API int pa_propagate(pa_ctx* ctx, const pa_path* path, void* field_dev, int b
  * [n_screens][batch][m], copied host->device inside the call) or from the device RNG (coef_host == NULL, seed /
  * realization0 / ring tables used).  The per-realization table [batch][out_stride] is copied to out_host and
  * the call returns after the stream has drained.  The field buffer is ctx workspace.  `batch` may be any size: the
- * library works through it in chunks (8 realizations at 2048^2) with one host->device copy of the coefficients up front
+ * library works through it in chunks (32 realizations at 2048^2) with one host->device copy of the coefficients up front
  * and one synchronisation at the end. */
 PA_API int pa_simulate_batch(pa_ctx* ctx, const pa_path* path, int batch, const float* fx_host, const float* fy_host,
                       const float* coef_host, unsigned long long seed, unsigned long long realization0,

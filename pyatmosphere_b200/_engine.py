@@ -322,7 +322,9 @@ class BlockRunner:
         torch = nat.torch_mod()
         ctx, lib, h = self.ctx, self.ctx.lib, self.ctx.handle
         dev, stride = ctx.tdevice, self.stride
-        seed, B0 = int(gpu.config["seed"]), max(1, int(gpu.config["batch"]))
+        # realizations per C call: the library works through a call in chunks of its own choosing (pa_simulate_batch*), so
+        # calls are made large; gpu.config['batch'] is only a lower bound here
+        seed, B0 = int(gpu.config["seed"]), max(256 if self.one_call else 1, int(gpu.config["batch"]))
         nm, nf, nt = len(nat.MEASURE_NAMES), len(self.fixed), len(self.tracked)
         raw = torch.empty((count, stride), dtype=torch.float64, device=dev)
         raw2 = torch.empty((count, stride), dtype=torch.float64, device=dev) if nt else None

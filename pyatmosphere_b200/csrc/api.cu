@@ -573,7 +573,9 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     c->seps.reserve(64);
     c->num_sms = prop.multiProcessorCount;
     c->use_tma = !direct;
-    c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") && atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0;
+    // row pass: the direct-access kernel everywhere except 8192^2 complex64, where one row is a whole 64 KiB tile and the
+    // TMA-fed ring is a little ahead (473 against 484 us; at 2048^2 / 4096^2 it loses: 145 / 234 against 132 / 150)
+    c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") ? atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0 : (n == 8192 && precision == PA_C64);
     c->sep_first_leg = !(getenv("PYATM_NO_ANALYTIC_LEG") && atoi(getenv("PYATM_NO_ANALYTIC_LEG")) != 0);
     *out = c;
     return PA_OK;
@@ -946,13 +948,13 @@ int pa_propagate(pa_ctx* c, const pa_path* p, void* field, int batch, const floa
 }
 
 // Realizations per pass of the fused path inside pa_simulate_batch*: a batch of any size is processed in chunks of this
-// many realizations (8 at 2048^2: 384 MiB of field + screen, larger than L2, and enough CTAs to fill the machine several
-// times over; more at smaller grids, where launch overhead would show; fewer at the long-haul sizes).  PYATM_SIM_CHUNK
-// overrides.
+// many realizations (32 at 2048^2: 1.5 GiB of field + screen and 2.4 GB of tensor-core operands; measured realizations/s
+// against the chunk size, device-resident: 4: 3056, 8: 3292, 16: 3385, 32: 3472 -- fewer launches and kernel tails per
+// realization; more at smaller grids, fewer at the long-haul sizes).  PYATM_SIM_CHUNK overrides.
 static int sim_chunk(const pa_ctx* c) {
     static const int forced = getenv("PYATM_SIM_CHUNK") ? atoi(getenv("PYATM_SIM_CHUNK")) : 0;
     if (forced > 0) return forced;
-    const long long want = 8LL * 2048 * 2048 / ((long long)c->n * c->n);
+    const long long want = 32LL * 2048 * 2048 / ((long long)c->n * c->n);
     return (int)(want < 2 ? 2 : (want > 64 ? 64 : want));
 }
 

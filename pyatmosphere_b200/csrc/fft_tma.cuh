@@ -25,7 +25,14 @@ constexpr int kSlots = 3;
 // store of the previous one has long left shared memory).  Two slots leave ~96 KiB of L1 for the twiddle / transfer-
 // function tables; measured per size (tools/prof_sizes.py, us per pass, 3 vs 2 slots): 1024: 46.5 / 50.4, 2048: 202.7 /
 // 202.1, 4096: 283.7 / 260.9, 8192 (split pass): 633 / 656 -> two slots at 4096 only.
+#ifdef PA_COL_SLOTS
+template <int N> struct ColSlots { static constexpr int value = PA_COL_SLOTS; };     // experiment switch
+#else
 template <int N> struct ColSlots { static constexpr int value = N == 4096 ? 2 : 3; };
+#endif
+#ifndef PA_COL_MINBLOCKS
+#define PA_COL_MINBLOCKS 2          // CTAs per SM the column kernel is compiled for when a tile needs <= 256 threads
+#endif
 #ifndef PA_TMA_ROW_THREADS
 #define PA_TMA_ROW_THREADS 128      // row pass: small CTAs (one 2048-point row each), several per SM
 #endif
@@ -168,7 +175,7 @@ __global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArg
 // exchanges that cross warps (first <-> second stage, forward and inverse); everything else is warp-local or an mbarrier the
 // warps arrive on without waiting: see ColAddrDual above.
 template <typename T, int N, int E>
-__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, TmaGeo<T, N, E>::THREADS <= 256 ? 2 : 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
+__global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, TmaGeo<T, N, E>::THREADS <= 256 ? PA_COL_MINBLOCKS : 1) k_cols_tma(const __grid_constant__ CUtensorMap tmap, ColArgs<T> a, int ntiles) {
     using C = cplx<T>;
     using G = TmaGeo<T, N, E>;
     constexpr int TC = G::TC, BOXR = G::BOXR, kColSlots = G::SLOTS;

@@ -271,3 +271,18 @@ def test_stats_allreduce_behind_the_c_abi_single_rank():
     assert torch.equal(hist.cpu(), torch.arange(200, dtype=torch.int64)) and sums.cpu().tolist() == [0.25, -3.0]
     assert len(comm.unique_id) == 128
     comm.close()
+
+
+def test_plane_source_through_a_vacuum_path():
+    """PlaneSource (sources.py:16-18; unusable with any path in the reference) is the field of ones here: a
+    plane wave stays a plane wave in vacuum and only picks up the carrier phase e^{ikL}."""
+    import pyatmosphere_b200 as pa
+    pa.gpu.config.update(use_gpu=True, dtype="complex128")
+    n, delta, wvl, length = 256, 2e-3, 808e-9, 1234.5
+    ch = pa.Channel(grid=pa.RectGrid(n, delta), source=pa.PlaneSource(wvl=wvl), path=pa.VacuumPath(length=length),
+                    pupil=pa.CirclePupil(radius=0.1))
+    out = ch.run(pupil=False).get()
+    import math
+    ang = 2 * math.pi / wvl * length                   # 9.6e9 rad: libm reduces it exactly (a float64 `% (2 pi)` would not)
+    want = complex(math.cos(ang), math.sin(ang))
+    assert out.shape == (n, n) and np.allclose(out, want, rtol=0, atol=1e-9)
