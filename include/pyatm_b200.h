@@ -150,6 +150,15 @@ PA_API int pa_simulate_batch(pa_ctx* ctx, const pa_path* path, int batch, const 
                       const float* coef_host, unsigned long long seed, unsigned long long realization0,
                       const float* ring_edges_dev, const float* ring_psd_dev, const float* pupils_host,
                       int npupil, double* out_host, int out_stride, void* stream);
+/* The same batch, enqueued only: the call returns as soon as the copies and kernels are on `stream` (simulations/
+ * simulation.py:89-114, as pa_simulate_batch).  The host buffers (pinned memory for the copies to be asynchronous) must stay
+ * untouched, and out_host unread, until pa_stream_synchronize (or any synchronisation of `stream`) returns; a host that
+ * enqueues batch i+1 before it waits for batch i keeps the GPU busy across the call boundary. */
+PA_API int pa_simulate_batch_async(pa_ctx* ctx, const pa_path* path, int batch, const float* fx_host, const float* fy_host,
+                            const float* coef_host, unsigned long long seed, unsigned long long realization0,
+                            const float* ring_edges_dev, const float* ring_psd_dev, const float* pupils_host,
+                            int npupil, double* out_host, int out_stride, void* stream);
+PA_API int pa_stream_synchronize(pa_ctx* ctx, void* stream);
 /* same, everything stays on the device and nothing synchronises (throughput loop); table_dev [batch][out_stride] */
 PA_API int pa_simulate_batch_device(pa_ctx* ctx, const pa_path* path, int batch, unsigned long long seed,
                              unsigned long long realization0, const float* ring_edges_dev,

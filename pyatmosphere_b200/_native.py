@@ -55,6 +55,9 @@ SIGNATURES = {
     "pa_propagate": (_int, [_vp, C.POINTER(PaPath), _vp, _int, _vp, _vp, _vp, _vp]),
     "pa_simulate_batch": (_int, [_vp, C.POINTER(PaPath), _int, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _int, _vp,
                                  _int, _vp]),
+    "pa_simulate_batch_async": (_int, [_vp, C.POINTER(PaPath), _int, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp, _int, _vp,
+                                       _int, _vp]),
+    "pa_stream_synchronize": (_int, [_vp, _vp]),
     "pa_simulate_batch_device": (_int, [_vp, C.POINTER(PaPath), _int, _u64, _u64, _vp, _vp, _vp, _int, _vp, _int,
                                         _vp]),
     "pa_comm_unique_id": (_int, [_vp]),

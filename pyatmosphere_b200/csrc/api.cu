@@ -1032,12 +1032,12 @@ static int simulate_common(pa_ctx* c, const pa_path* p, int batch, const float* 
     return PA_OK;
 }
 
-int pa_simulate_batch(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,
-                      unsigned long long seed, unsigned long long realization0, const float* edges, const float* psd,
-                      const float* pupils_host, int npupil, double* out_host, int out_stride, void* stream) {
+// enqueue only: host -> device copies, the whole batch, the table's device -> host copy; nothing waits
+static int simulate_host_enqueue(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,
+                                 unsigned long long seed, unsigned long long realization0, const float* edges, const float* psd,
+                                 const float* pupils_host, int npupil, double* out_host, int out_stride, cudaStream_t st) {
     PA_REQUIRE(c && p && out_host && batch > 0, "bad arguments to pa_simulate_batch");
     PA_REQUIRE(coef_host || (edges && psd) || p->n_screens == 0, "either host coefficients or ring tables are required");
-    cudaStream_t st = (cudaStream_t)stream;
     int rc = grow((void**)&c->table, &c->table_bytes, (size_t)batch * out_stride * sizeof(double));
     if (rc) return rc;
     rc = grow((void**)&c->pupils, &c->pupils_bytes, (size_t)(npupil > 0 ? npupil : 1) * 3 * sizeof(float));
@@ -1047,7 +1047,31 @@ int pa_simulate_batch(pa_ctx* c, const pa_path* p, int batch, const float* fx_ho
                          out_stride, st);
     if (rc) return rc;
     PA_CUDA(cudaMemcpyAsync(out_host, c->table, (size_t)batch * out_stride * sizeof(double), cudaMemcpyDeviceToHost, st));
+    return PA_OK;
+}
+
+int pa_simulate_batch(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,
+                      unsigned long long seed, unsigned long long realization0, const float* edges, const float* psd,
+                      const float* pupils_host, int npupil, double* out_host, int out_stride, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = simulate_host_enqueue(c, p, batch, fx_host, fy_host, coef_host, seed, realization0, edges, psd, pupils_host, npupil, out_host,
+                                   out_stride, st);
+    if (rc) return rc;
     PA_CUDA(cudaStreamSynchronize(st));
+    return PA_OK;
+}
+
+int pa_simulate_batch_async(pa_ctx* c, const pa_path* p, int batch, const float* fx_host, const float* fy_host, const float* coef_host,
+                            unsigned long long seed, unsigned long long realization0, const float* edges, const float* psd,
+                            const float* pupils_host, int npupil, double* out_host, int out_stride, void* stream) {
+    return simulate_host_enqueue(c, p, batch, fx_host, fy_host, coef_host, seed, realization0, edges, psd, pupils_host, npupil, out_host,
+                                 out_stride, (cudaStream_t)stream);
+}
+
+int pa_stream_synchronize(pa_ctx* c, void* stream) {
+    PA_REQUIRE(c != nullptr, "bad arguments to pa_stream_synchronize: null context");
+    PA_CUDA(cudaSetDevice(c->device));
+    PA_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return PA_OK;
 }
 

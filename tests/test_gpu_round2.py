@@ -286,3 +286,43 @@ def test_plane_source_through_a_vacuum_path():
     ang = 2 * math.pi / wvl * length                   # 9.6e9 rad: libm reduces it exactly (a float64 `% (2 pi)` would not)
     want = complex(math.cos(ang), math.sin(ang))
     assert out.shape == (n, n) and np.allclose(out, want, rtol=0, atol=1e-9)
+
+
+def test_async_batches_equal_the_synchronous_call():
+    """pa_simulate_batch_async: two batches enqueued back to back (pinned host buffers, separate result tables), one
+    pa_stream_synchronize; records equal those of two synchronous pa_simulate_batch calls.  The batch (40) spans several
+    internal chunks at this size."""
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact", theta_cut=2.0)
+    p = dict(load_golden("turb128")["params"], n=2048, delta=2.5e-4)        # 2048^2: chunks of 32 realizations
+    ch = build_channel(pa, p)
+    ch.path.init_phase_screens()
+    ctx = eng.channel_context(ch)
+    desc = ch.path._descriptor((0, 0), through_output=False, from_field=False)
+    S, M, B = p["count"], p["m"], 40
+    stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+    rng = np.random.default_rng(5)
+    pup = torch.from_numpy(np.array([[np.float32(p["pupil"] ** 2), 0, 0]], dtype=np.float32)).pin_memory()
+    sets = []
+    for _ in range(2):
+        np.random.seed(int(rng.integers(1 << 30)))
+        fx, fy, cf = eng.draw_spectra_numpy(ch.path, B)
+        sets.append([torch.from_numpy(np.ascontiguousarray(a.transpose(1, 0, 2))).pin_memory() for a in (fx, fy)] +
+                    [torch.from_numpy(np.ascontiguousarray(cf.transpose(1, 0, 2)).view(np.float32).copy()).pin_memory()])
+    sync_out = [np.zeros((B, stride)) for _ in range(2)]
+    for k in range(2):
+        fx, fy, cf = sets[k]
+        nat.check(ctx.lib.pa_simulate_batch(ctx.handle, desc.ref(), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), 0, 0, None, None, nat.ptr(pup),
+                                            1, nat.ptr(sync_out[k]), stride, nat.stream_ptr()))
+    async_out = [torch.zeros((B, stride), dtype=torch.float64).pin_memory() for _ in range(2)]
+    for k in range(2):
+        fx, fy, cf = sets[k]
+        nat.check(ctx.lib.pa_simulate_batch_async(ctx.handle, desc.ref(), B, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), 0, 0, None, None,
+                                                  nat.ptr(pup), 1, nat.ptr(async_out[k]), stride, nat.stream_ptr()))
+    nat.check(ctx.lib.pa_stream_synchronize(ctx.handle, nat.stream_ptr()))
+    for k in range(2):
+        assert np.array_equal(async_out[k].numpy(), sync_out[k])
+        assert np.all(np.abs(sync_out[k][:, 0] - 1.0) < 1e-4)              # total power of every realization
+    assert not np.array_equal(sync_out[0], sync_out[1])

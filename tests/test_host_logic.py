@@ -306,7 +306,7 @@ def test_header_cites_the_reference_for_every_compute_entry_point():
     hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
     utilities = {"pa_version", "pa_last_error", "pa_device_count", "pa_launch_count", "pa_ctx_destroy", "pa_ctx_permutation",
                  "pa_ctx_fft_geometry", "pa_fft_pass", "pa_phase_to_turns", "pa_simulate_batch_device", "pa_comm_unique_id",
-                 "pa_comm_create", "pa_comm_destroy"}
+                 "pa_comm_create", "pa_comm_destroy", "pa_stream_synchronize"}
     cite = re.compile(r"[\w/]+\.py:\d+")
     last_comment = ""
     checked = 0
