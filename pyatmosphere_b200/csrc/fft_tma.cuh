@@ -92,6 +92,16 @@ template <int N, int E, int TC> struct ColAddrDual {
     }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
+// the same map with a hook that runs in front of every block-wide exchange barrier (the column kernel hands its deferred TMA
+// store to it: see k_cols_tma)
+template <int N, int E, int TC, typename Hook> struct ColAddrDualHook : ColAddrDual<N, E, TC> {
+    Hook* hook;
+    __device__ __forceinline__ ColAddrDualHook(int c_, Hook* h) : ColAddrDual<N, E, TC>{c_}, hook(h) {}
+    __device__ __forceinline__ void sync() const {
+        (*hook)();
+        __syncthreads();
+    }
+};
 
 
 template <typename T, int N, int E, bool IN_PERM, bool OUT_PERM>
@@ -219,7 +229,19 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, TmaGeo<T, N, E>::THR
         issue_load(0);
         issue_load(1);
     }
-    const ColAddrDual<N, E, TC> addr{c};
+    // Deferred store (2048- and 4096-row tiles; measured 158.0 -> 154.7 / 225.6 -> 219.0 us, but 622.9 -> 649.3 for the
+    // 256-row tiles of the split pass and 39.0 -> 39.6 at 1024): the TMA store of tile k is issued by thread 0 in front of
+    // the first block-wide barrier of tile k+1, when every warp has certainly left tile k -- so warp 0 never waits for the
+    // others at the end of a tile (which made the hand-over a third block-wide meeting point).
+    constexpr bool kLateStore = N >= 2048;
+    int pending_store = -1;
+    auto hook = [&]() {
+        if (kLateStore && threadIdx.x == 0 && pending_store >= 0) {
+            issue_store(pending_store);
+            pending_store = -1;
+        }
+    };
+    const ColAddrDualHook<N, E, TC, decltype(hook)> addr(c, &hook);
     for (int k = 0;; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) break;
@@ -255,14 +277,25 @@ __global__ void __launch_bounds__(TmaGeo<T, N, E>::THREADS, TmaGeo<T, N, E>::THR
         __syncwarp();
         if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(done0 + 8 * slot);
         if (threadIdx.x == 0) {
-            issue_store(k);
-            if constexpr (kColSlots >= 3) {
-                ptx::bulk_wait_read<1>();                  // the store of tile k-1 has left its slot ...
-                issue_load(k + 2);                         // ... which is the slot of tile k+2
+            if constexpr (kLateStore) {
+                if constexpr (kColSlots >= 3) {
+                    ptx::bulk_wait_read<0>();              // the store of tile k-1 (issued early in this tile) has left its slot ...
+                    issue_load(k + 2);                     // ... which is the slot of tile k+2
+                }
+                pending_store = k;
+            } else {
+                issue_store(k);
+                if constexpr (kColSlots >= 3) {
+                    ptx::bulk_wait_read<1>();              // the store of tile k-1 has left its slot ...
+                    issue_load(k + 2);                     // ... which is the slot of tile k+2
+                }
             }
         }
     }
-    if (threadIdx.x == 0) ptx::bulk_wait_read<0>();
+    if (threadIdx.x == 0) {
+        if (pending_store >= 0) issue_store(pending_store);
+        ptx::bulk_wait_read<0>();
+    }
 }
 
 }  // namespace pa
