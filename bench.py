@@ -382,35 +382,39 @@ def run_c3(args):
                 "per_kernel_frac": {k: alg / v / 1e9 / peak for k, v in times.items()},
                 "stage_us_per_realization": sum(times.values()) * 1e6 / Br,
                 "stage_frac_of_hbm_roofline": (8 * n * n * 8 * Br) / sum(times.values()) / 1e9 / peak}
-        # ---- tensor-pipe roofline of the screen synthesis (pa_screen_ss, tcgen05 path): 8 screens per call, preparation
-        # kernels included.  Executed MMA flops = 3 split-fp16 products x 2 N^2 K2 (K2 = 2 x high rings, padded to 32);
-        # algorithmic flops = 4 N^2 M.  Peak = measured dense bf16 cuBLAS throughput (same pipe, same rate).
+        # ---- tensor-pipe roofline of the screen synthesis (pa_screen_ss, tcgen05 path): 32 screens per call -- what one path
+        # position of a chunk of the step asks for -- preparation kernels included.  Executed MMA flops = 3 split-fp16 products
+        # x 2 N^2 K2 (K2 = 2 x high rings, padded to 32); algorithmic flops = 4 N^2 M.  Peak = measured dense
+        # bf16 cuBLAS throughput (same pipe, same rate).
         try:
             m_split, degree = ps0.low_ring_plan()
             method = eng.screen_method(n)
             if method == nat.PA_SCREEN_TC:
-                fx_d = torch.empty((Br, M), dtype=torch.float32, device=dev)
+                Bs = 32
+                turns_s = torch.empty((Bs, n, n), dtype=torch.float32, device=dev)
+                fx_d = torch.empty((Bs, M), dtype=torch.float32, device=dev)
                 fy_d = torch.empty_like(fx_d)
-                cf_d = torch.empty((Br, M, 2), dtype=torch.float32, device=dev)
-                nat.check(lib.pa_rng_spectrum(h, 99, 0, Br, 0, 1, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d),
+                cf_d = torch.empty((Bs, M, 2), dtype=torch.float32, device=dev)
+                nat.check(lib.pa_rng_spectrum(h, 99, 0, Bs, 0, 1, M, nat.ptr(edges_d), nat.ptr(psd_d), nat.ptr(fx_d), nat.ptr(fy_d),
                                               nat.ptr(cf_d), stream))
                 bound = eng.coef_bound(ps0._ring_power(), m_split)
 
                 def screens():
-                    nat.check(lib.pa_screen_ss(h, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), M, m_split, degree, 0.0, 0.0, Br,
-                                               nat.ptr(turns), None, 0, method, bound, stream))
+                    nat.check(lib.pa_screen_ss(h, nat.ptr(fx_d), nat.ptr(fy_d), nat.ptr(cf_d), M, m_split, degree, 0.0, 0.0, Bs,
+                                               nat.ptr(turns_s), None, 0, method, bound, stream))
                 for _ in range(3):
                     screens()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 torch.cuda.synchronize()
                 a.record()
-                for _ in range(20):
+                for _ in range(10):
                     screens()
                 b.record()
                 torch.cuda.synchronize()
-                t_scr = a.elapsed_time(b) / 20 * 1e-3
+                t_scr = a.elapsed_time(b) / 10 * 1e-3
+                del turns_s
                 k2 = -(-2 * (M - m_split) // 32) * 32
-                mma_flops = 3 * 2.0 * n * n * k2 * Br
+                mma_flops = 3 * 2.0 * n * n * k2 * Bs
                 try:
                     with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
                         tpeak, tsrc = float(json.load(f)["bf16_tflops"]), "measured cuBLAS bf16 burst (MEASURED_PEAKS.json)"
@@ -418,7 +422,8 @@ def run_c3(args):
                     tpeak, tsrc = 2250.0, "nominal dense bf16 (no MEASURED_PEAKS.json)"
                 roof_screen = {"bound": "tensor", "kernel": "pa_screen_ss (k_factors_tc + polynomial nodes + k_screen_tc)",
                                "achieved": mma_flops / t_scr / 1e12, "peak": tpeak, "unit": "TFLOP/s", "frac": mma_flops / t_scr / 1e12 / tpeak,
-                               "peak_source": tsrc, "us_per_screen": t_scr * 1e6 / Br, "executed_mma_flops_per_screen": mma_flops / Br,
+                               "peak_source": tsrc, "screens_per_call": Bs, "us_per_screen": t_scr * 1e6 / Bs,
+                               "executed_mma_flops_per_screen": mma_flops / Bs,
                                "algorithmic_flops_per_screen": 4.0 * n * n * M, "rings_in_contraction": int(M - m_split),
                                "rings_as_polynomial": int(m_split)}
         except Exception as e:          # noqa: BLE001  (an extra, never fatal for the bench line)

@@ -97,6 +97,8 @@ struct pa_ctx {
     double* rowsums = nullptr; size_t rowsums_bytes = 0;   // per-row sums of the fused final pass
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
+    cudaStream_t aux = nullptr;                           // second stream: operand generation next to the polynomial kernels
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int* perm_dev = nullptr;                              // device copy of `perm` (FFT phase screens)
     void* fftws = nullptr; size_t fftws_bytes = 0;        // subharmonic tables and mean partials of the FFT phase screens
     int num_sms = 148;
@@ -486,13 +488,27 @@ static int screens(pa_ctx* c, const float* fx, const float* fy, const float* coe
         a.p_scale = ldexp(1.0, e);
         const size_t need = screen_tc_workspace(n, m, m_split, tc_total > 0 ? tc_total : nscreens);
         PA_REQUIRE(c->tcws_bytes >= need, "tensor-core screen workspace not reserved");
-        if (tc_phase != 1) {            // polynomial coefficients belong to the preparation phase
-            int rc = launch_screen_poly(a, st);
+        static const bool fork = !(getenv("PYATM_TC_FORK") && atoi(getenv("PYATM_TC_FORK")) == 0);
+        cudaStream_t fstream = nullptr;
+        if (tc_phase != 1) {            // preparation phase
+            if (fork && a.degree >= 0) {
+                // fork: the operand generation (HBM-store-bound) runs on the context's second stream while the polynomial
+                // coefficients and node tables (float64, latency-bound small grids) run on `st`; joined before the contraction
+                if (!c->aux) {
+                    PA_CUDA(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
+                    PA_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+                    PA_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+                }
+                PA_CUDA(cudaEventRecord(c->ev_fork, st));
+                PA_CUDA(cudaStreamWaitEvent(c->aux, c->ev_fork, 0));
+                fstream = c->aux;
+            }
+            int rc = launch_screen_poly(a, st);      // polynomial coefficients
             if (rc) return check_launch(rc, "screen polynomial");
         }
         static const int swap = getenv("PYATM_TC_SWAP") ? atoi(getenv("PYATM_TC_SWAP")) : 0;
-        note(tc_phase == 1 ? 1 : (tc_phase == 0 ? 3 : 4));
-        return check_launch(launch_screen_tc(a, c->tcws, c->tc_err, c->num_sms, swap, st, tc_phase, tc_first, tc_total),
+        note(tc_phase == 1 ? 1 : (tc_phase == 0 ? 5 : 6));      // preparation: polynomial coefficients, operands, three node kernels
+        return check_launch(launch_screen_tc(a, c->tcws, c->tc_err, c->num_sms, swap, st, tc_phase, tc_first, tc_total, fstream, c->ev_join),
                             "tensor-core screen synthesis");
     }
     note(3);
@@ -593,6 +609,9 @@ int pa_ctx_destroy(pa_ctx* c) {
     }
     for (auto& t : c->seps)
         if (t.dev) cudaFree(t.dev);
+    if (c->aux) cudaStreamDestroy(c->aux);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     delete c;
     return PA_OK;
 }

@@ -35,7 +35,10 @@ int screen_init_constants();
 int launch_screen_exact(const ScreenLaunch& a, cudaStream_t st);
 int launch_screen_poly(const ScreenLaunch& a, cudaStream_t st);
 size_t screen_tc_workspace(int n, int m, int m_split, int nscreens);
+// factors_stream (optional): the operand generation of the preparation phase is launched there instead of `st`; the caller
+// has made it wait for everything earlier on `st` and joins it back before the contraction (api.cu: screens()).
 int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st, int phase = 2,
-                     int first_screen = 0, int total_screens = -1);
+                     int first_screen = 0, int total_screens = -1, cudaStream_t factors_stream = nullptr,
+                     cudaEvent_t factors_done = nullptr);
 
 }  // namespace pa

@@ -779,7 +779,7 @@ size_t screen_tc_workspace(int n, int m, int m_split, int nscreens) {
 // [first_screen, first_screen + a.nscreens) of a workspace laid out for total_screens); 1 = contraction only for those
 // screens (their operands must have been prepared); 2 = both.
 int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int num_sms, int swap, cudaStream_t st, int phase,
-                     int first_screen, int total_screens) {
+                     int first_screen, int total_screens, cudaStream_t factors_stream, cudaEvent_t factors_done) {
     using namespace tc;
     if (a.n % TN != 0) return (int)cudaErrorInvalidValue;
     const int nhigh = a.m - a.m_split;
@@ -809,7 +809,9 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
     if (phase == 0 || phase == 2) {
         dim3 gf(a.n / 128, 2 * a.nscreens, KF_SPLIT);
         const size_t kf_smem = ((size_t)(kpad / 2 + 3) / 4 * 4) * sizeof(float) + (size_t)(kpad / 2) * sizeof(float2);
-        k_factors_tc<<<gf, 128, kf_smem, st>>>(a, P, Q, kpad, pair ? 1 : 0);
+        // store-bound operand generation next to the float64 / latency-bound polynomial kernels below, on a stream of its own
+        k_factors_tc<<<gf, 128, kf_smem, factors_stream ? factors_stream : st>>>(a, P, Q, kpad, pair ? 1 : 0);
+        if (factors_stream && factors_done) cudaEventRecord(factors_done, factors_stream);
         if (a.degree >= 0) {
             dim3 gu((nq + 127) / 128, a.degree + 1, a.nscreens);
             k_poly_rows<<<gu, 128, 0, st>>>(a, U, u_stride, nq);
@@ -818,6 +820,7 @@ int launch_screen_tc(const ScreenLaunch& a, void* workspace, int* err_flag, int 
         }
         dim3 gn(a.n / 128, (nq + NODES_PT - 1) / NODES_PT, a.nscreens);
         k_poly_nodes<<<gn, 128, 0, st>>>(a, U, u_stride, nodes, jit, nq);
+        if (factors_stream && factors_done) cudaStreamWaitEvent(st, factors_done, 0);      // join: operands ready for `st`
         if (phase == 0) return (int)cudaGetLastError();
     }
     static SmemOptIn attr_done, attr_done_pair;
