@@ -35,12 +35,12 @@ class Channel:
         return self.pupil.output(out) if pupil else out
 
     def generator(self, pupil=True, store_output=True, *args, **kwargs):
+        """Per-slab (field, screen) pairs of the path (channels.py:37-44); the field behind the last leg is kept in
+        `self.output` (behind the aperture if `pupil`) unless `store_output` is off."""
         self.output = None
+        final = yield from self.path.generator(self.source.output(), *args, **kwargs)
         if store_output:
-            path_output = yield from self.path.generator(self.source.output(), *args, **kwargs)
-            self.output = self.pupil.output(path_output) if pupil else path_output
-        else:
-            yield from self.path.generator(self.source.output(), *args, **kwargs)
+            self.output = self.pupil.output(final) if pupil else final
 
     def get_rythov2(self):
         return get_rytov2(self.path.phase_screen.model.Cn2, self.source.k, self.path.length)
