@@ -25,6 +25,9 @@ block = full[start:start + shares[rank]]
 assert np.array_equal(dist.all_gather_blocks(block, shares), full)
 import torch
 assert np.array_equal(dist.all_gather_blocks(torch.as_tensor(block), shares), full)
+# ragged: fewer rows than ranks -- the last rank owns nothing
+few = full[:1]
+assert np.array_equal(dist.all_gather_blocks(few if rank == 0 else few[:0], [1] + [0] * (world - 1)), few)
 stats = dist.reduce_statistics(full[mine], cols, eta_names=[("fixed", 0.1)])
 bw2 = full[:, cols["mean_x"]] ** 2
 lt2 = 4 * full[:, cols["mean_x2"]]

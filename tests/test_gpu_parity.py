@@ -389,9 +389,11 @@ def test_full_size_turbulent_energy_and_determinism():
     assert rel_l2(fields["complex64"], fields["complex128"]) < 1e-5
 
 
-def test_fused_statistics_route_equals_literal_route(monkeypatch):
+@pytest.mark.parametrize("apertures", [[], [0.12], [0.12, 0.05], [0.12, 0.05, 0.2, 0.01], [0.12, 0.05, 0.2, 0.01, 0.3]])
+def test_fused_statistics_route_equals_literal_route(monkeypatch, apertures):
     """The Monte-Carlo route (analytic first leg, reductions fused into the final row pass, no field written) gives
-    the same records as the literal route (source pass, six full legs, separate measure sweep)."""
+    the same records as the literal route (source pass, six full legs, separate measure sweep), for every number of
+    apertures the fused pass is compiled for (0..4) and beyond (5: separate sweep again)."""
     from pyatmosphere_b200 import _engine as eng, _native as nat
     g = load_golden("quick256")
     p = dict(g["params"], n=512, delta=2e-3)       # 512: smallest size with the fused final pass
@@ -404,8 +406,8 @@ def test_fused_statistics_route_equals_literal_route(monkeypatch):
         nat.clear_contexts()
         pa = _pa("complex64", rng="philox", seed=7, batch=4)
         ch = build_channel(pa, p)
-        cols = eng.table_columns([p["pupil"], 0.05], [])
-        tables[tag] = eng.simulate_realizations(ch, 0, 4, np.arange(4), [p["pupil"], 0.05], [])
+        cols = eng.table_columns(sorted(apertures), [])
+        tables[tag] = eng.simulate_realizations(ch, 0, 4, np.arange(4), sorted(apertures), [])
         assert tables[tag].shape == (4, len(cols))
     nat.clear_contexts()
     assert np.allclose(tables["fused"], tables["literal"], rtol=2e-5, atol=1e-8)

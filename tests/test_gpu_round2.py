@@ -326,3 +326,23 @@ def test_async_batches_equal_the_synchronous_call():
         assert np.array_equal(async_out[k].numpy(), sync_out[k])
         assert np.all(np.abs(sync_out[k][:, 0] - 1.0) < 1e-4)              # total power of every realization
     assert not np.array_equal(sync_out[0], sync_out[1])
+
+
+def test_block_route_with_tiny_and_unequal_record_counts():
+    """One realization, and results that want different numbers of records (README: BeamResult 2000, PDTResult 6000): every
+    Measure stops at its own max_size, the records are prefixes of one another's run."""
+    import pyatmosphere_b200 as pa
+    pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact", theta_cut=2.0, rng="philox", seed=21, batch=4)
+    p = load_golden("turb128")["params"]
+    ch = build_channel(pa, p)
+    one = pa.simulations.PDTResult(ch, max_size=1)
+    pa.simulations.Simulation([one]).run()
+    assert len(one.measures[0]) == 1
+    beam = pa.simulations.BeamResult(ch, max_size=3)
+    pdt = pa.simulations.PDTResult(ch, max_size=7)
+    sim = pa.simulations.Simulation([beam, pdt])
+    sim.run()
+    assert [len(m) for m in beam.measures] == [3] * 6 and len(pdt.measures[0]) == 7 and sim.realizations_done == 7
+    assert pdt.measures[0].data[0] == one.measures[0].data[0]
+    sim.run()                                           # nothing left to do: no new records, no error
+    assert len(pdt.measures[0]) == 7
