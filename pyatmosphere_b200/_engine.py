@@ -144,9 +144,36 @@ def table_columns(pupils_fixed, pupils_tracked):
 def draw_spectra_numpy(path, count):
     """`count` realizations x S screens drawn from numpy's global RNG in the reference's order (realization-major,
     then screen; per screen random(1), random(M), normal(2,M)).  Returns fx, fy [count][S][M] float32 and
-    coef [count][S][M] complex64."""
+    coef [count][S][M] complex64.
+
+    Paths made of plain SSPhaseScreens over one frequency grid take the raw numbers screen by screen (three RNG calls
+    each, nothing else inside the loop) and turn them into (fx, fy, coef) with whole-array operations afterwards -- the
+    same elementwise float32 / complex64 arithmetic as grids.py:98-119 and phase_screens.py:98-103, so the results are
+    bit-identical to the per-screen route below (tests/test_host_logic.py) at a fifth of the host time."""
     screens = path.phase_screens
     S, M = len(screens), screens[0].f_grid.points
+    from .phase_screens import SSPhaseScreen
+    if all(type(ps) is SSPhaseScreen and ps.f_grid is screens[0].f_grid for ps in screens):
+        shared = np.empty((count, S, 1), dtype=np.float32)
+        angle = np.empty((count, S, M), dtype=np.float32)
+        normal = np.empty((count, S, 2, M), dtype=np.float64)
+        rnd, nrm = np.random.random, np.random.normal
+        for r in range(count):
+            for s in range(S):
+                shared[r, s] = rnd(size=(1,))
+                angle[r, s] = rnd(size=(M,))
+                normal[r, s] = nrm(size=(2, M))
+        for ps in screens:
+            ps.cache_clear()
+        outer = screens[0].f_grid.base                                   # float32
+        inner = np.insert(outer, 0, 0)[:-1]
+        rho = np.sqrt(inner**2 + shared * (outer**2 - inner**2))         # grids.py:98-102, float32 throughout
+        theta = 2 * np.pi * angle                                        # grids.py:104-107
+        fx = rho * np.cos(theta)
+        fy = rho * np.sin(theta)
+        amp = np.stack([np.sqrt(ps._get_psd()) for ps in screens])       # [S][M] float32
+        cf = (normal[:, :, 0] + 1j * normal[:, :, 1]).astype(np.complex64) * amp      # phase_screens.py:101-102
+        return fx, fy, cf
     fx = np.empty((count, S, M), dtype=np.float32)
     fy = np.empty((count, S, M), dtype=np.float32)
     cf = np.empty((count, S, M), dtype=np.complex64)
