@@ -568,6 +568,8 @@ def run_c3(args):
             "roofline": roof, "roofline_screen": roof_screen, "cpu_baseline": cpu, "stats_check": stats,
         }
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     d.close()
 
 
