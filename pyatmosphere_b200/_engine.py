@@ -302,6 +302,54 @@ def simulate_realizations(channel, first, count, mine, pupils_fixed, pupils_trac
     return out
 
 
+class HostBatch:
+    """One batch of realizations with HOST-drawn coefficients (numpy RNG mode), enqueued and not waited for: the spectra are
+    drawn from numpy's global RNG in the reference's order when the object is made, copied to pinned memory and handed to
+    pa_simulate_batch_async; `result()` waits for the batch and returns its rows.  Simulation.run keeps one HostBatch in
+    flight, so the (RNG-bound) drawing of batch k+1 overlaps the GPU work of batch k.  Statistics-only route: fixed
+    apertures (at most nat.MAX_PUPILS), no tracked ones."""
+
+    def __init__(self, channel, first, count, mine, pupils_fixed):
+        torch = nat.torch_mod()
+        self.count, self.mine, self.first = int(count), np.asarray(mine), int(first)
+        self.cols = table_columns(pupils_fixed, [])
+        self.nf = len(pupils_fixed)
+        path = channel.path
+        path.init_phase_screens()
+        host = draw_spectra_numpy(path, count)            # every rank draws the whole batch: identical RNG streams
+        self.B = B = len(self.mine)
+        self.event = None
+        if B == 0:
+            return
+        ctx = channel_context(channel)
+        sel = slice(int(self.mine[0] - first), int(self.mine[0] - first) + B)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()      # noqa: E731
+        self.fx = pin(host[0][sel].transpose(1, 0, 2))                                # [S][B][M]
+        self.fy = pin(host[1][sel].transpose(1, 0, 2))
+        self.cf = pin(np.ascontiguousarray(host[2][sel].transpose(1, 0, 2)).view(np.float32))
+        tab = np.array([[np.float32(r**2), 0, 0] for r in pupils_fixed], dtype=np.float32).reshape(-1, 3)
+        self.tab = pin(tab) if len(tab) else None
+        self.stride = nat.MEASURE_HEAD + nat.MAX_PUPILS
+        self.out = torch.empty((B, self.stride), dtype=torch.float64).pin_memory()
+        self.desc = path._descriptor((0, 0), through_output=False, from_field=False)
+        nat.check(ctx.lib.pa_simulate_batch_async(ctx.handle, self.desc.ref(), B, nat.ptr(self.fx), nat.ptr(self.fy), nat.ptr(self.cf), 0, 0,
+                                                  None, None, nat.ptr(self.tab), self.nf, nat.ptr(self.out), self.stride, nat.stream_ptr()))
+        self.event = torch.cuda.Event()
+        self.event.record()
+
+    def result(self):
+        """Rows of this rank's share, [len(mine)][len(cols)] float64 (waits for the batch)."""
+        out = np.zeros((self.B, len(self.cols)), dtype=np.float64)
+        if self.B == 0:
+            return out
+        self.event.synchronize()
+        raw = self.out.numpy()
+        nm = len(nat.MEASURE_NAMES)
+        out[:, :nm] = raw[:, :nm]
+        out[:, nm:] = raw[:, nat.MEASURE_HEAD:nat.MEASURE_HEAD + self.nf]
+        return out
+
+
 class BlockRunner:
     """Device-RNG Monte-Carlo blocks with NOTHING but kernel launches between the first and the last realization: every
     batch is enqueued on the current stream (pa_simulate_batch_device, or pa_rng_spectrum + pa_propagate + pa_measure when

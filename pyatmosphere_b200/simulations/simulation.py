@@ -150,6 +150,52 @@ class Simulation:
                 m.data.append(float(table[r, cols[name]]))
         self.realizations_done += count
 
+    def _fast_keys(self):
+        ms = list(self.flattened_measures())
+        fixed = sorted({m.fast_key[1] for m in ms if m.fast_key[0] == "pupil_eta" and m.fast_key[2] == "fixed"})
+        tracked = sorted({m.fast_key[1] for m in ms if m.fast_key[0] == "pupil_eta" and m.fast_key[2] == "tracked"})
+        return ms, fixed, tracked
+
+    def _append_rows(self, ms, table, cols, count):
+        for m in ms:
+            if m.is_done:
+                continue
+            key = m.fast_key
+            name = key[1] if key[0] == "moment" else (key[2], key[1])
+            take = count if m.max_size is None else min(count, m.max_size - len(m))
+            m.data.extend(table[:take, cols[name]].tolist())
+
+    def pipelined_host_batches(self, plot_step, save_step):
+        """numpy-RNG mode with statistics-only records: batches of gpu.config['batch'] realizations per rank, ONE in flight --
+        the spectra of batch k+1 are drawn (numpy's legacy generator, the bottleneck of this mode) while the GPU runs batch k.
+        The draws happen in the reference's order whatever the pipelining, and exactly as many as the run needs."""
+        channel = next(iter(self.measures))
+        ms, fixed, _ = self._fast_keys()
+        world, rank = dist.world_rank()
+        iteration, pending = 0, None
+        while True:
+            left = self.remaining()
+            ahead = pending.count if pending is not None else 0
+            nxt = None
+            if left is None or left - ahead > 0:
+                count = gpu.config["batch"] * world
+                count = count if left is None else min(count, left - ahead)
+                for step in (plot_step, save_step):      # a batch never steps across a multiple of the plot / save step
+                    if step:
+                        count = min(count, step - (iteration + ahead) % step)
+                first = self.realizations_done + ahead
+                mine = dist.shard_indices(first, count, rank, world)
+                nxt = eng.HostBatch(channel, first, count, mine, fixed)
+            if pending is not None:
+                table = dist.gather_rows(pending.result(), pending.mine - pending.first, pending.count)
+                self._append_rows(ms, table, pending.cols, pending.count)
+                self.realizations_done += pending.count
+                iteration += pending.count
+                self.process_output(iteration, plot_step=plot_step, save_step=save_step)
+            pending = nxt
+            if pending is None:
+                return
+
     def iter_block(self, count):
         """`count` device-RNG realizations: this rank's contiguous share runs with nothing but kernel launches in between
         (engine BlockRunner), then one all-gather hands every rank the whole table."""
@@ -186,6 +232,10 @@ class Simulation:
             iteration = 0
             use_batch = self.batchable() and gpu.config["batch"] > 1
             use_block = self.batchable() and gpu.config["rng"] != "numpy"
+            if use_batch and not use_block:
+                _, fixed, tracked = self._fast_keys()
+                if not tracked and len(fixed) <= nat.MAX_PUPILS:
+                    self.pipelined_host_batches(plot_step, save_step)
             while not self.is_measures_done():
                 if use_block:
                     left = self.remaining()
