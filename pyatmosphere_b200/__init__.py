@@ -21,4 +21,4 @@ from .theory.models import *  # noqa: F401,F403
 # `from pyatmosphere import *` exports exactly these two names in the reference too (__init__.py:14-17); every other
 # name above is reachable by explicit import, as there
 __all__ = ["Channel", "QuickChannel"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"
