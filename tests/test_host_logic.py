@@ -417,3 +417,21 @@ def test_uniform_ring_powers_detects_unequal_slabs():
     ch2.path.init_phase_screens()
     assert ch2.path._fusable() and not eng.uniform_ring_powers(ch2.path.phase_screens)
     assert np.allclose(thick._get_psd(), 3 * thin._get_psd(), rtol=1e-5)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/pyatm_b200.h is a C header (the boundary the reference's ctypes / cffi / cgo-style binding would consume): it
+    compiles as C99 with no C++ or CUDA types, and a C translation unit can take the address of every declared function."""
+    import shutil
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
+    names = sorted(set(re.findall(r"PA_API[^;(]*?\b(pa_\w+)\s*\(", hdr)))
+    assert len(names) == len(nat.SIGNATURES) == 30
+    src = tmp_path / "use.c"
+    src.write_text('#include "pyatm_b200.h"\n' + "void* table[] = {" + ", ".join(f"(void*){n}" for n in names) + "};\n" +
+                   "int main(void) { pa_path p; p.n_screens = 0; return (int)sizeof(table) * 0 + p.n_screens; }\n")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                        "-o", str(tmp_path / "use.o")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
