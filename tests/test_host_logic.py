@@ -435,3 +435,21 @@ def test_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-Wno-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src),
                         "-o", str(tmp_path / "use.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_plain_c_host_example_links_against_the_library(tmp_path):
+    """examples/c_host.c (a host with no Python, torch or CUDA headers) compiles as C99 and links against the shipped
+    library; without a batch file it prints its usage and exits 2 (the GPU run is tests/test_gpu_c_host.py)."""
+    import shutil
+    import subprocess
+    from pyatmosphere_b200 import _native as nat
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(os.path.abspath(nat.LIB_PATH))
+    exe = str(tmp_path / "c_host")
+    subprocess.run(["gcc", "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_host.c"), "-o", exe, "-L", libdir, "-lpyatm_b200",
+                    f"-Wl,-rpath,{libdir}"], check=True)
+    run = subprocess.run([exe], capture_output=True, text=True)
+    assert run.returncode == 2 and "usage" in run.stderr
