@@ -1,0 +1,136 @@
+"""Size-independent properties of the vacuum leg and of the screen synthesis at the benchmarked sizes (2048^2 and 8192^2),
+where the float64 oracle takes too long to run per case.  The leg u -> IFFT2( H_L * FFT2(u) ) (pathes.py:27-40,
+theory/vacuum.py:5-7) is linear and unitary, legs compose (H_L1 * H_L2 = H_(L1+L2)) and conj(leg(conj(v))) is its
+inverse; the sparse-spectrum screen (phase_screens.py:108-136) is linear in its coefficients.
+
+Tolerances (relative L2): complex64 4e-6 (two to three legs of float32 transforms, each measured 3e-7 .. 7e-7 against
+the oracle in test_gpu_parity.py), complex128 1e-13 (1e-12 for composition); screens 1e-5 rad-relative as in test_gpu_screen_tc.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(2048, "complex64"), (2048, "complex128"), (4096, "complex64"), (8192, "complex64")]
+
+
+@pytest.fixture(autouse=True)
+def _cfg():
+    import pyatmosphere_b200 as pa
+    saved = dict(pa.gpu.config)
+    yield
+    pa.gpu.config.clear()
+    pa.gpu.config.update(saved)
+    from pyatmosphere_b200 import _native as nat
+    import torch
+    nat.clear_contexts()
+    torch.cuda.empty_cache()
+
+
+def _setup(n, dtype):
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    pa.gpu.config.update(use_gpu=True, dtype=dtype)
+    ctx = eng.grid_context(pa.RectGrid(n, 1.5e-3))
+    cdt = torch.complex64 if dtype == "complex64" else torch.complex128
+    g = torch.Generator(device="cuda").manual_seed(n + len(dtype))
+
+    def rand():
+        # band-limited-ish random field with a Gaussian envelope: |u| spans several decades like a propagated beam
+        ax = (torch.arange(n, device="cuda", dtype=torch.float64) - n / 2) / (n / 6)
+        env = torch.exp(-(ax[:, None] ** 2 + ax[None, :] ** 2))
+        re = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
+        im = torch.randn((n, n), dtype=torch.float64, device="cuda", generator=g)
+        return (torch.complex(re, im) * env).to(cdt).reshape(1, n, n).contiguous()
+
+    def leg(u, length):
+        v = u.clone()
+        nat.check(ctx.lib.pa_vacuum_leg(ctx.handle, nat.ptr(v), v.shape[0], float(length), 808e-9, nat.stream_ptr()))
+        return v
+
+    def rel(a, b):
+        a, b = a.to(torch.complex128), b.to(torch.complex128)
+        return float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(b))
+
+    return rand, leg, rel, (4e-6 if dtype == "complex64" else 1e-13)
+
+
+@pytest.mark.parametrize("n,dtype", CASES)
+def test_leg_is_linear_unitary_and_composes(n, dtype):
+    import torch
+    rand, leg, rel, tol = _setup(n, dtype)
+    u, v = rand(), rand()
+    a, b = 0.75 - 0.5j, -1.25 + 2.0j
+    L1, L2 = 7.0e3, 1.3e4
+    lu = leg(u, L1)
+    # unitary: the transfer function has modulus one and the transform pair is normalised (utils.py:42-50)
+    nu, nlu = float(torch.linalg.vector_norm(u.to(torch.complex128))), float(torch.linalg.vector_norm(lu.to(torch.complex128)))
+    assert abs(nlu / nu - 1) < tol, (n, dtype, nlu / nu - 1)
+    # linear
+    err_lin = rel(leg(a * u + b * v, L1), a * lu + b * leg(v, L1))
+    # legs compose -- up to the carrier phase: exp(ik L1) exp(ik L2) and exp(ik (L1 + L2)) differ by the float64 rounding of
+    # k L ~ 1.6e11 rad (ulp 3e-5 rad), in the reference (theory/vacuum.py:6, evaluated in float64) as much as here
+    two, one = leg(lu, L2).to(torch.complex128), leg(u, L1 + L2).to(torch.complex128)
+    carrier = torch.vdot(one.flatten(), two.flatten())
+    carrier = carrier / carrier.abs()
+    assert abs(float(torch.angle(carrier))) < 1e-4
+    err_comp = rel(two, one * carrier)
+    # inverse through conjugation: conj(leg(conj(w))) = leg_{-L}(w)
+    err_inv = rel(torch.conj(leg(torch.conj(lu).contiguous(), L1)), u)
+    print(f"{n}^2 {dtype}: linearity {err_lin:.2e}, composition {err_comp:.2e} (carrier {float(torch.angle(carrier)):.1e} rad), "
+          f"round trip {err_inv:.2e}")
+    # the transfer-function phase pi L lambda f^2 reaches ~1e4 rad at the grid corner (float64 ulp 2e-12 rad), and L1, L2 and
+    # L1 + L2 round it differently: composition in complex128 holds to 1e-12, not 1e-13
+    assert err_lin < tol and err_comp < max(tol, 1e-12) and err_inv < tol, (err_lin, err_comp, err_inv)
+
+
+@pytest.mark.parametrize("n,dtype", CASES)
+def test_batched_legs_equal_single_legs(n, dtype):
+    """A batch is a set of independent fields: every field of a batched call equals its own single call bit for bit."""
+    import torch
+    rand, leg, rel, tol = _setup(n, dtype)
+    B = 3 if n <= 4096 else 2
+    us = torch.cat([rand() for _ in range(B)], dim=0).contiguous()
+    out = leg(us, 9.0e3)
+    for i in range(B):
+        assert torch.equal(out[i], leg(us[i:i + 1].contiguous(), 9.0e3)[0]), (n, dtype, i)
+
+
+@pytest.mark.parametrize("method", ["tc", "exact"])
+def test_full_size_screen_is_linear_in_its_coefficients(method):
+    """phi[c1 + c2] = phi[c1] + phi[c2] at 2048^2 with 1024 rings, split between polynomial and contraction as in production, full phase output."""
+    import torch
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import _engine as eng, _native as nat
+    pa.gpu.config.update(use_gpu=True, dtype="complex64")
+    n, m = 2048, 1024
+    ctx = eng.grid_context(pa.RectGrid(n, 1.5e-3))
+    rng = np.random.default_rng(5)
+    f = np.exp(np.linspace(np.log(1 / 15000), np.log(333.3), m))
+    th = rng.random(m) * 2 * np.pi
+    fx = torch.as_tensor((f * np.cos(th)).astype(np.float32), device="cuda")
+    fy = torch.as_tensor((f * np.sin(th)).astype(np.float32), device="cuda")
+    sd = 0.5 * (f / f[0]) ** (-1 / 2)                               # ring amplitudes: 0.5 rad down to 2e-4 rad
+    c1 = ((rng.standard_normal(m) + 1j * rng.standard_normal(m)) * sd).astype(np.complex64)
+    c2 = ((rng.standard_normal(m) + 1j * rng.standard_normal(m)) * sd).astype(np.complex64)
+    meth = nat.PA_SCREEN_TC if method == "tc" else nat.PA_SCREEN_EXACT
+    # the production split: low rings (small arguments, large amplitudes) as a float64 polynomial, the rest contracted;
+    # psd = (2 sd)^2 so that the plan's amplitude bounds hold for c1 + c2 as well
+    ext = n / 2 * 1.5e-3
+    m_split, degree = eng.plan_low_rings(f, (2 * sd) ** 2, ext, ext, eng.theta_cut(n), eng.screen_tolerance())
+    bound = eng.coef_bound((2 * sd) ** 2, m_split)
+    assert method != "tc" or 0 < m_split < m
+
+    def phi(c):
+        cf = torch.as_tensor(np.ascontiguousarray(c).view(np.float32), device="cuda")
+        turns = torch.empty((1, n, n), dtype=torch.float32, device="cuda")
+        out = torch.empty((1, n, n), dtype=torch.float32, device="cuda")
+        nat.check(ctx.lib.pa_screen_ss(ctx.handle, nat.ptr(fx), nat.ptr(fy), nat.ptr(cf), m, m_split, degree, 0.0, 0.0, 1, nat.ptr(turns),
+                                       nat.ptr(out), 0, meth, bound, nat.stream_ptr()))
+        return out[0].double()
+
+    p1, p2, p12 = phi(c1), phi(c2), phi((c1.astype(np.complex128) + c2).astype(np.complex64))
+    err = float(torch.linalg.vector_norm(p12 - p1 - p2) / torch.linalg.vector_norm(p12 - p12.mean()))   # vs the part that varies
+    worst = float((p12 - p1 - p2).abs().max())
+    print(f"screen linearity ({method}): rel-L2 {err:.2e}, max {worst:.2e} rad (rms phase {float(p12.std()):.2f} rad)")
+    assert err < 1e-5, err
