@@ -69,6 +69,18 @@ PA_API int pa_source_gaussian(pa_ctx* ctx, void* field_dev, int batch, double w0
  * In place, natural order in and out; length <= 0 leaves the field untouched. */
 PA_API int pa_vacuum_leg(pa_ctx* ctx, void* field_dev, int batch, double length, double wvl, void* stream);
 
+/* utils.py:42-44 fft2 (forward != 0) and utils.py:47-50 ifft2 (forward == 0): the centred two-dimensional transform pair,
+ * index N/2 = origin / zero frequency on both sides, natural order in and out.
+ *   forward:  out[p][q] = scale * sum_ij in[i][j] exp(-2 pi i ((i-N/2)(p-N/2) + (j-N/2)(q-N/2)) / N)      (fft2: scale = delta^2)
+ *   inverse:  the same with exp(+...)                                                          (ifft2: scale = delta_f^2)
+ * in_dev, out_dev: [batch][N][N] complex (context precision); in_dev == out_dev is allowed. */
+PA_API int pa_fft2c(pa_ctx* ctx, const void* in_dev, void* out_dev, int batch, int forward, double scale, void* stream);
+
+/* theory/sources.py:16-18 GaussianBeam.amplitude on caller-supplied squared radii:
+ * out[i] = sqrt(2/pi)/w0 * exp(-(1/w0^2 + i k/(2 F0)) r2[i]);  r2_dev: float32 (PA_C64 ctx) or float64 (PA_C128). */
+PA_API int pa_gaussian_amplitude(pa_ctx* ctx, const void* r2_dev, void* out_dev, size_t count, double w0, double wvl, double F0,
+                          void* stream);
+
 /* phase_screens.py:108-136 SSPhaseScreen.generate_phase_screen (real part, :25-28).
  * fx, fy: [nscreens][m] float32; coef: [nscreens][m] complex64 (interleaved); rings sorted by radius.
  * m_split / degree: rings below m_split are summed as a float64 polynomial of that total degree

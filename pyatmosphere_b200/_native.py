@@ -42,6 +42,8 @@ SIGNATURES = {
     "pa_ctx_fft_geometry": (_int, [_vp, _vp]),
     "pa_source_gaussian": (_int, [_vp, _vp, _int, _dbl, _dbl, _dbl, _vp]),
     "pa_vacuum_leg": (_int, [_vp, _vp, _int, _dbl, _dbl, _vp]),
+    "pa_fft2c": (_int, [_vp, _vp, _vp, _int, _int, _dbl, _vp]),
+    "pa_gaussian_amplitude": (_int, [_vp, _vp, _vp, _sz, _dbl, _dbl, _dbl, _vp]),
     "pa_screen_ss": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _dbl, _dbl, _int, _vp, _vp, _int, _int, _dbl, _vp]),
     "pa_screen_fft": (_int, [_vp, _vp, _int, _vp, _int, _vp, _vp, _vp]),
     "pa_apply_screen": (_int, [_vp, _vp, _int, _vp, _dbl, _vp]),
@@ -188,6 +190,17 @@ def context(n: int, delta: float, x: np.ndarray, y: np.ndarray, precision: int, 
         ctx = Context(device, int(n), int(precision), x, y, delta)
         _contexts[key] = ctx
     return ctx
+
+
+def any_context(precision: int) -> Context:
+    """Some context of this precision on the current device -- for the element-wise entry points that need a device and a
+    precision but no grid (pa_gaussian_amplitude); a small one is created when none exists yet."""
+    device = torch_mod().cuda.current_device()
+    for (dev, _n, prec, _delta), ctx in _contexts.items():
+        if dev == device and prec == int(precision):
+            return ctx
+    axis = (np.arange(64, dtype=np.float32) - 32) * 1.0
+    return context(64, 1.0, axis, axis, precision, device)
 
 
 def clear_contexts():

@@ -779,6 +779,53 @@ int pa_screen_fft(pa_ctx* c, const void* spectrum, int nscreens, const double* t
     return check_launch(launch_fftscreen_finish(c->prec, a, st), "FFT screen finish");
 }
 
+// utils.py:42-50: the centred transform pair.  Both directions run the inverse half of the split-step passes (as
+// pa_screen_fft does): S(v)[i][j] = sum_pq v[p][q] e^{+2 pi i ((i-c)(p-c) + (j-c)(q-c)) / N}, c = N/2, is the unnormalised
+// centred inverse, and the forward transform is conj(S(conj(u))).
+int pa_fft2c(pa_ctx* c, const void* in, void* out, int batch, int forward, double scale, void* stream) {
+    PA_REQUIRE(c && in && out && batch > 0, "bad arguments to pa_fft2c");
+    PA_CUDA(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n = c->n;
+    const size_t plane = (size_t)n * n;
+    int rc = grow(&c->field, &c->field_bytes, (size_t)batch * plane * c->csize());
+    if (rc) return rc;
+    if (!c->perm_dev) {
+        PA_CUDA(cudaMalloc((void**)&c->perm_dev, (size_t)n * sizeof(int)));
+        PA_CUDA(cudaMemcpy(c->perm_dev, c->perm.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    }
+    note(1);
+    rc = check_launch(launch_fft2c_gather(c->prec, in, c->field, c->perm_dev, n, batch, forward != 0, st), "fft2c gather");
+    if (rc) return rc;
+    ColLaunch cl;
+    cl.field = c->field;
+    cl.tw = c->tw;
+    cl.hp = nullptr;
+    cl.alpha_re = scale;
+    cl.alpha_im = 0.0;
+    cl.batch = batch;
+    cl.tmap = nullptr;
+    cl.num_sms = c->num_sms;
+    cl.inv_only = true;
+    note(1);
+    rc = check_launch(launch_cols(c->prec, n, cl, st), "fft2c column pass");
+    if (rc) return rc;
+    rc = rows(c, c->field, batch, true, false, false, nullptr, 1.0, 0, 0, 0, st);
+    if (rc) return rc;
+    note(1);
+    return check_launch(launch_copy_conj(c->prec, c->field, out, (size_t)batch * plane, forward != 0, st), "fft2c finish");
+}
+
+// theory/sources.py:16-18 GaussianBeam.amplitude on caller-supplied squared radii
+int pa_gaussian_amplitude(pa_ctx* c, const void* r2, void* out, size_t count, double w0, double wvl, double F0, void* stream) {
+    PA_REQUIRE(c && r2 && out && count > 0 && w0 > 0 && wvl > 0, "bad arguments to pa_gaussian_amplitude");
+    PA_CUDA(cudaSetDevice(c->device));
+    double amp, aw, ac;
+    source_params(w0, wvl, F0, &amp, &aw, &ac);
+    note(1);
+    return check_launch(launch_gaussian_amplitude(c->prec, r2, out, count, amp, aw, ac, (cudaStream_t)stream), "gaussian amplitude");
+}
+
 int pa_apply_screen(pa_ctx* c, void* field, int batch, const void* turns, double scale, void* stream) {
     PA_REQUIRE(c && field && batch > 0, "bad arguments to pa_apply_screen");
     return rows(c, field, batch, false, false, false, turns, scale, 0, 0, 0, (cudaStream_t)stream);

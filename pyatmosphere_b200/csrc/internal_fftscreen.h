@@ -26,5 +26,7 @@ struct FftScreenLaunch {
 int launch_fftscreen_gather(int prec, const FftScreenLaunch& a, cudaStream_t st);
 int launch_fftscreen_finish(int prec, const FftScreenLaunch& a, cudaStream_t st);
 int fftscreen_finish_launches(const FftScreenLaunch& a);
+// centred spectrum / field -> storage order with the (-1)^(p+q) modulation, optionally conjugated (pa_fft2c)
+int launch_fft2c_gather(int prec, const void* in, void* ws, const int* perm, int n, int batch, bool conj, cudaStream_t st);
 
 }  // namespace pa

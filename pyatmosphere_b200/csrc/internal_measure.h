@@ -31,6 +31,8 @@ int launch_measure(int prec, const MeasureLaunch& a, cudaStream_t st);
 int launch_measure_rows(const double* rowsums, const float* y, int n, int batch, double delta2, int npupil, double* out, int out_stride,
                         cudaStream_t st);
 int launch_intensity(int prec, const void* u, void* out, size_t count, cudaStream_t st);
+int launch_copy_conj(int prec, const void* in, void* out, size_t count, bool conj, cudaStream_t st);
+int launch_gaussian_amplitude(int prec, const void* r2, void* out, size_t count, double amp, double aw, double ac, cudaStream_t st);
 int launch_pupil(int prec, const void* in, void* out, const float* x, const float* y, int n, int batch, float r2, float sx, float sy, cudaStream_t st);
 int launch_phase_to_turns(const void* phi, int phi_f64, void* turns, int turns_f64, size_t count, cudaStream_t st);
 int launch_histogram(const double* values, size_t stride, size_t count, const double* edges, int nbins, unsigned long long* counts, cudaStream_t st);

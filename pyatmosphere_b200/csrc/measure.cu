@@ -178,6 +178,38 @@ int launch_intensity(int prec, const void* u, void* out, size_t count, cudaStrea
     return (int)cudaGetLastError();
 }
 
+// out = in or conj(in)   (last step of pa_fft2c)
+template <typename T> __global__ void k_copy_conj(const cplx<T>* in, cplx<T>* out, size_t count, bool conj) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        cplx<T> v = in[i];
+        if (conj) v.y = -v.y;
+        out[i] = v;
+    }
+}
+int launch_copy_conj(int prec, const void* in, void* out, size_t count, bool conj, cudaStream_t st) {
+    const int blocks = (int)((count + 255) / 256 < 148 * 16 ? (count + 255) / 256 : 148 * 16);
+    if (prec == 0) k_copy_conj<float><<<blocks, 256, 0, st>>>((const float2*)in, (float2*)out, count, conj);
+    else k_copy_conj<double><<<blocks, 256, 0, st>>>((const double2*)in, (double2*)out, count, conj);
+    return (int)cudaGetLastError();
+}
+
+// theory/sources.py:16-18  amp * exp(-(aw + i ac) r2), evaluated in float64 and rounded once
+template <typename T> __global__ void k_gaussian_amplitude(const T* r2, cplx<T>* out, size_t count, double amp, double aw, double ac) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+        const double q = (double)r2[i];
+        const double mag = amp * exp(-aw * q);
+        double sn, cs;
+        sincos(ac * q, &sn, &cs);
+        out[i] = mkc<T>((T)(mag * cs), (T)(-mag * sn));
+    }
+}
+int launch_gaussian_amplitude(int prec, const void* r2, void* out, size_t count, double amp, double aw, double ac, cudaStream_t st) {
+    const int blocks = (int)((count + 255) / 256 < 148 * 16 ? (count + 255) / 256 : 148 * 16);
+    if (prec == 0) k_gaussian_amplitude<float><<<blocks, 256, 0, st>>>((const float*)r2, (float2*)out, count, amp, aw, ac);
+    else k_gaussian_amplitude<double><<<blocks, 256, 0, st>>>((const double*)r2, (double2*)out, count, amp, aw, ac);
+    return (int)cudaGetLastError();
+}
+
 // out = in * [(x - sx)^2 + (y + sy)^2 <= r^2]   (pupils.py:8-13), float32 compare like the reference
 template <typename T>
 __global__ void k_pupil(const cplx<T>* in, cplx<T>* out, const float* x, const float* y, int n, int batch, float r2, float sx, float sy) {

@@ -17,7 +17,8 @@ constexpr int kGatherThreads = 256;
 constexpr int kAddThreads = 256;
 
 // ws[b][py][px] = (-1)^(perm[py] + perm[px]) * cn[b][(perm[py] + n/2) % n][(perm[px] + n/2) % n]
-template <typename T>
+// CONJ: the conjugate of the input is gathered (the forward transform of pa_fft2c is conj(inverse(conj(.))))
+template <typename T, bool CONJ = false>
 __global__ void __launch_bounds__(kGatherThreads) k_fftscreen_gather(const cplx<T>* __restrict__ cn, cplx<T>* __restrict__ ws,
                                                                       const int* __restrict__ perm, int n) {
     const int px = blockIdx.x * kGatherThreads + threadIdx.x;
@@ -30,6 +31,7 @@ __global__ void __launch_bounds__(kGatherThreads) k_fftscreen_gather(const cplx<
         v.x = -v.x;
         v.y = -v.y;
     }
+    if (CONJ) v.y = -v.y;
     ws[plane + (size_t)py * n + px] = v;
 }
 
@@ -172,5 +174,17 @@ int launch_fftscreen_finish(int prec, const FftScreenLaunch& a, cudaStream_t st)
     return prec == 0 ? finish_t<float>(a, st) : finish_t<double>(a, st);
 }
 int fftscreen_finish_launches(const FftScreenLaunch& a) { return a.ngroups > 0 ? 4 : 3; }
+
+int launch_fft2c_gather(int prec, const void* in, void* ws, const int* perm, int n, int batch, bool conj, cudaStream_t st) {
+    const dim3 grid((n + kGatherThreads - 1) / kGatherThreads, n, batch);
+    if (prec == 0) {
+        if (conj) k_fftscreen_gather<float, true><<<grid, kGatherThreads, 0, st>>>((const cplx<float>*)in, (cplx<float>*)ws, perm, n);
+        else k_fftscreen_gather<float, false><<<grid, kGatherThreads, 0, st>>>((const cplx<float>*)in, (cplx<float>*)ws, perm, n);
+    } else {
+        if (conj) k_fftscreen_gather<double, true><<<grid, kGatherThreads, 0, st>>>((const cplx<double>*)in, (cplx<double>*)ws, perm, n);
+        else k_fftscreen_gather<double, false><<<grid, kGatherThreads, 0, st>>>((const cplx<double>*)in, (cplx<double>*)ws, perm, n);
+    }
+    return (int)cudaGetLastError();
+}
 
 }  // namespace pa

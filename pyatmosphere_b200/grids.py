@@ -31,6 +31,22 @@ class RectGrid(Grid):
         return -n // 2 + odd, n // 2 + odd
 
     @property
+    def _left_bound(self):
+        return self._bounds(0)[0]
+
+    @property
+    def _right_bound(self):
+        return self._bounds(0)[1]
+
+    @property
+    def _top_bound(self):
+        return self._bounds(1)[0]
+
+    @property
+    def _bottom_bound(self):
+        return self._bounds(1)[1]
+
+    @property
     def shape(self):
         return self.resolution
 

@@ -1,6 +1,7 @@
 """Descriptors that wire the parts of a channel together, and the container of a drawn spectrum.
-Behavioural mirror of /root/reference/pyatmosphere/utils.py:7-39 (the centred fft2/ifft2 helpers of
-utils.py:42-50 live in the native library: see _native / pathes.VacuumPath)."""
+Behavioural mirror of /root/reference/pyatmosphere/utils.py:7-39; the centred fft2/ifft2 helpers of utils.py:42-50 are
+calls into the native library (pa_fft2c) -- the split-step path itself never uses them, its legs are fused passes
+(pathes.VacuumPath -> pa_vacuum_leg)."""
 from __future__ import annotations
 
 from dataclasses import dataclass
@@ -46,3 +47,37 @@ class PolarDiscreteFunction:
     rho: Sequence[float]
     theta: Sequence[float]
     value: Sequence[float]
+
+
+def _centred_transform(data, delta, scale, forward):
+    """[N][N] or [batch][N][N] complex array (host or device) -> DeviceArray of the same shape; see pa_fft2c."""
+    import numpy as np
+
+    from . import _engine as eng
+    from . import _native as nat
+    from . import gpu
+    from .grids import RectGrid
+    gpu.require_gpu()
+    torch = nat.torch_mod()
+    t = data.t if isinstance(data, gpu.DeviceArray) else torch.as_tensor(np.asarray(data), device="cuda")
+    if t.ndim not in (2, 3) or t.shape[-1] != t.shape[-2]:
+        raise ValueError("fft2 / ifft2 take square [N][N] (or [batch][N][N]) arrays")
+    n = int(t.shape[-1])
+    ctx = eng.grid_context(RectGrid(n, float(delta)))
+    src = t.to(ctx.cdtype).reshape(-1, n, n).contiguous()
+    out = torch.empty_like(src)
+    nat.check(ctx.lib.pa_fft2c(ctx.handle, nat.ptr(src), nat.ptr(out), int(src.shape[0]), int(forward), float(scale),
+                               nat.stream_ptr()))
+    return gpu.DeviceArray(out.reshape(tuple(t.shape)))
+
+
+def fft2(x, delta):
+    """utils.py:42-44: fftshift(fft2(fftshift(x))) * delta**2 (grid sizes are even, so fftshift == ifftshift)."""
+    return _centred_transform(x, delta, float(delta) ** 2, True)
+
+
+def ifft2(x, delta):
+    """utils.py:47-50: ifftshift(ifft2(ifftshift(x))) * (N * delta)**2 with numpy's 1/N**2 inside ifft2, i.e. the plain
+    sum times delta**2; `delta` is the frequency step, the spatial step of the context is 1 / (N * delta)."""
+    n = int(x.shape[-1])
+    return _centred_transform(x, 1.0 / (n * float(delta)), float(delta) ** 2, False)

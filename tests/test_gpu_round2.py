@@ -7,7 +7,7 @@ import types
 import numpy as np
 import pytest
 
-from conftest import load_golden
+from conftest import load_golden, rel_l2
 from test_gpu_parity import build_channel
 
 pytestmark = pytest.mark.gpu
@@ -346,3 +346,71 @@ def test_block_route_with_tiny_and_unequal_record_counts():
     assert pdt.measures[0].data[0] == one.measures[0].data[0]
     sim.run()                                           # nothing left to do: no new records, no error
     assert len(pdt.measures[0]) == 7
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+@pytest.mark.parametrize("n", [64, 256, 2048])
+def test_centred_transform_pair_of_utils(dtype, n):
+    """utils.fft2 / utils.ifft2 (utils.py:42-50) through pa_fft2c against numpy's definition in complex128, their round
+    trip, and theory.vacuum.vacuum_propagation (theory/vacuum.py:5-7) against the oracle's leg."""
+    import pyatmosphere_b200 as pa
+    from pyatmosphere_b200 import utils
+    from pyatmosphere_b200.theory.vacuum import vacuum_propagation
+    from oracle import splitstep as orc
+    saved = dict(pa.gpu.config)
+    try:
+        pa.gpu.config.update(use_gpu=True, dtype=dtype)
+        rng = np.random.default_rng(n)
+        delta = 1.5e-3
+        df = 1.0 / (n * delta)
+        u = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(dtype)
+        tol = 2e-6 if dtype == "complex64" else 1e-12
+        want_f = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(u.astype(np.complex128)))) * delta**2
+        got_f = utils.fft2(u, delta)
+        assert got_f.shape == (n, n) and got_f.dtype == np.dtype(dtype)
+        assert rel_l2(got_f.get(), want_f) < tol
+        want_i = np.fft.ifftshift(np.fft.ifft2(np.fft.ifftshift(u.astype(np.complex128)))) * (n * df) ** 2
+        assert rel_l2(utils.ifft2(u, df).get(), want_i) < tol
+        assert rel_l2(utils.ifft2(got_f, df).get(), u) < 2 * tol                      # device array in, round trip
+        batch = np.stack([u, 2j * u])
+        assert rel_l2(utils.fft2(batch, delta).get()[1], 2j * want_f) < tol             # [batch][N][N]
+        # the reference's free function for one leg
+        wvl, length = 808e-9, 3.0e3
+        x, y = orc.rect_xy(n, delta)
+        beam = orc.gaussian_source(x, y, 0.02 * n * delta * 10, wvl, mode="f64") * np.exp(1j * rng.standard_normal((n, n)) * 0.1)
+        want = orc.vacuum_leg(beam, length, wvl, delta, mode="f64")
+        f2 = None
+        got = vacuum_propagation(beam.astype(dtype), length, 2 * np.pi / wvl, delta, f2, df)
+        assert rel_l2(got.get(), want) < (1e-5 if dtype == "complex64" else 1e-10)
+        with pytest.raises(ValueError):
+            vacuum_propagation(beam, length, 2 * np.pi / wvl, delta, f2, 2 * df)
+    finally:
+        pa.gpu.config.clear()
+        pa.gpu.config.update(saved)
+
+
+@pytest.mark.parametrize("dtype", ["complex64", "complex128"])
+def test_gaussian_beam_amplitude_on_given_radii(dtype):
+    """theory/sources.py:16-18 through pa_gaussian_amplitude; equals GaussianSource.output() on the channel grid's rho^2."""
+    import pyatmosphere_b200 as pa
+    from oracle import splitstep as orc
+    saved = dict(pa.gpu.config)
+    try:
+        pa.gpu.config.update(use_gpu=True, dtype=dtype)
+        n, delta, wvl, w0, F0 = 256, 2e-3, 808e-9, 0.03, 4.0e3
+        ch = pa.Channel(grid=pa.RectGrid(n, delta), source=pa.GaussianSource(wvl=wvl, w0=w0, F0=F0),
+                        path=pa.VacuumPath(length=1e3), pupil=pa.CirclePupil(radius=1.0))
+        rho2 = ch.grid.get_rho2()
+        got = ch.source.amplitude(rho2)
+        assert got.shape == (n, n) and got.dtype == np.dtype(dtype)
+        x, y = orc.rect_xy(n, delta)
+        want = orc.gaussian_source(x, y, w0, wvl, F0, mode="f64")
+        # rho^2 arrives in float32 as the reference forms it (grids.py:71-73): the curvature phase k rho^2 / (2 F0) ~ 1e2 rad
+        # carries its rounding, 6e-8 * 1e2 rad, in complex64 and complex128 alike
+        assert rel_l2(got.get(), want) < 2e-5
+        assert rel_l2(got.get(), ch.source.output().get()) < 2e-5
+        g64 = pa.sources.GaussianSource(wvl=wvl, w0=w0, F0=np.inf).amplitude((x**2 + y**2).astype(np.float64))   # float32 rho^2, promoted: the oracle's
+        assert rel_l2(g64.get(), orc.gaussian_source(x, y, w0, wvl, np.inf, mode="f64")) < (2e-7 if dtype == "complex64" else 1e-14)
+    finally:
+        pa.gpu.config.clear()
+        pa.gpu.config.update(saved)

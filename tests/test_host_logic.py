@@ -428,7 +428,7 @@ def test_header_is_plain_c(tmp_path):
         pytest.skip("no gcc")
     hdr = open(os.path.join(ROOT, "include", "pyatm_b200.h")).read()
     names = sorted(set(re.findall(r"PA_API[^;(]*?\b(pa_\w+)\s*\(", hdr)))
-    assert len(names) == len(nat.SIGNATURES) == 30
+    assert len(names) == len(nat.SIGNATURES) == 32
     src = tmp_path / "use.c"
     src.write_text('#include "pyatm_b200.h"\n' + "void* table[] = {" + ", ".join(f"(void*){n}" for n in names) + "};\n" +
                    "int main(void) { pa_path p; p.n_screens = 0; return (int)sizeof(table) * 0 + p.n_screens; }\n")
@@ -453,3 +453,50 @@ def test_plain_c_host_example_links_against_the_library(tmp_path):
                     f"-Wl,-rpath,{libdir}"], check=True)
     run = subprocess.run([exe], capture_output=True, text=True)
     assert run.returncode == 2 and "usage" in run.stderr
+
+
+def test_every_symbol_of_the_scope_table_is_importable_under_the_reference_names():
+    """SURVEY.md section 8(a) rows a1-a14 and (f) n1-n4, symbol by symbol, under the reference's module paths."""
+    import importlib
+    surface = {
+        "pyatmosphere.grids": ["RectGrid.get_x", "RectGrid.get_y", "RectGrid.get_xy", "RectGrid.get_rho2", "RectGrid.get_f_grid",
+                               "RectGrid.origin_index", "RectGrid.extent", "RectGrid._left_bound", "RectGrid._right_bound",
+                               "RectGrid._top_bound", "RectGrid._bottom_bound", "RandLogPolarGrid.base", "RandLogPolarGrid.get_rho",
+                               "RandLogPolarGrid.get_theta", "RandLogPolarGrid.get_xy"],
+        "pyatmosphere.sources": ["GaussianSource.output", "PlaneSource"],
+        "pyatmosphere.theory.sources": ["GaussianBeam.amplitude", "GaussianBeam.get_w", "GaussianBeam.get_theta0",
+                                        "GaussianBeam.get_Lambda0", "GaussianBeam.get_theta", "GaussianBeam.get_Lambda"],
+        "pyatmosphere.theory.vacuum": ["vacuum_propagation"],
+        "pyatmosphere.theory.models": ["MVKModel.psd_n", "Model.psd_phi_f"],
+        "pyatmosphere.utils": ["fft2", "ifft2", "CrossRef", "Default", "PolarDiscreteFunction"],
+        "pyatmosphere.pathes": ["VacuumPath.lossless_output", "PhaseScreensPath.generator", "PhaseScreensPath.lossless_output",
+                                "AbstractPath.output", "AbstractPath.append_losses", "IdenticalPhaseScreensPath"],
+        "pyatmosphere.phase_screens": ["SSPhaseScreen.generate_phase_screen", "SSPhaseScreen.generate", "SSPhaseScreen._get_spectrum",
+                                       "SSPhaseScreen._get_psd", "SSPhaseScreen.cache_clear", "SUPhaseScreen", "FFTPhaseScreen",
+                                       "WindSUPhaseScreen"],
+        "pyatmosphere.pupils": ["CirclePupil.get_pupil", "CirclePupil.output"],
+        "pyatmosphere.measures": ["I", "eta", "mean_x", "mean_y", "mean_x2", "mean_xy", "mean_y2"],
+        "pyatmosphere.channels": ["Channel.run", "Channel.generator", "Channel.get_rythov2", "QuickChannel"],
+        "pyatmosphere.gpu": ["config", "get_xp", "get_array"],
+        "pyatmosphere.simulations.simulation": ["Simulation.run", "Simulation.iter"],
+        "pyatmosphere.simulations.measure": ["Measure"],
+        "pyatmosphere.simulations.result": ["Result.save_output", "Result.load_output"],
+        "pyatmosphere.simulations.beam": ["BeamResult"],
+        "pyatmosphere.simulations.pdt": ["PDTResult", "TrackedPDTResult"],
+        "pyatmosphere.simulations.si": ["SIResult"],
+        "pyatmosphere.simulations.wind": ["TimeCoherenceResult", "TimeBWcorrSimulation"],
+    }
+    missing = []
+    for module, names in surface.items():
+        mod = importlib.import_module(module)
+        for dotted in names:
+            node = mod
+            for part in dotted.split("."):
+                if not hasattr(node, part):
+                    missing.append(f"{module}:{dotted}")
+                    break
+                node = getattr(node, part)
+    assert not missing, missing
+    g = importlib.import_module("pyatmosphere.grids").RectGrid((5, 8), 0.5)
+    assert (g._left_bound, g._right_bound, g._top_bound, g._bottom_bound) == (-2, 3, -4, 4)       # grids.py:36-50
+    assert list(g.extent) == [-1.0, 1.5, -2.0, 2.0]
