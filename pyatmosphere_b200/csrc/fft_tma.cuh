@@ -39,6 +39,9 @@ template <int N> struct ColSlots { static constexpr int value = N == 4096 ? 2 : 
 #ifndef PA_TMA_COL_BYTES
 #define PA_TMA_COL_BYTES 65536      // column pass: 64 KiB tiles (4 columns of 2048 complex64)
 #endif
+#ifndef PA_TMA_COL_BYTES_256
+#define PA_TMA_COL_BYTES_256 32768  // 256-row tiles (256^2 grids, inner transform of the split pass): 32 KiB, two CTAs per SM (8192^2 complex128: 1326 -> 1250 us)
+#endif
 
 // geometry of the row pass: FPB rows per tile so that a CTA has about PA_TMA_ROW_THREADS threads
 template <typename T, int N, int E> struct TmaRowGeo {
@@ -55,7 +58,7 @@ template <typename T, int N, int E> struct TmaRowGeo {
 template <typename T, int N, int E> struct TmaGeo {
     using C = cplx<T>;
     static constexpr int TPF = N / E;
-    static constexpr int TC = PA_TMA_COL_BYTES / (N * (int)sizeof(C));
+    static constexpr int TC = (N == 256 ? PA_TMA_COL_BYTES_256 : PA_TMA_COL_BYTES) / (N * (int)sizeof(C));
     static constexpr int THREADS = TC * TPF;
     static constexpr int SLOT = TC * N * (int)sizeof(C);
     static constexpr int BOXR = N < 256 ? N : 256;                          // rows per tensor box
