@@ -15,6 +15,10 @@
 #pragma once
 #include "fft_core.cuh"
 
+#ifndef PA_OUTER_THREADS_F64
+#define PA_OUTER_THREADS_F64 64
+#endif
+
 namespace pa {
 
 // exp(-2 pi i k / 32), k = 0..15; the switch folds once the calling loop is unrolled
@@ -67,18 +71,22 @@ template <typename T> __device__ __forceinline__ void dft32_inv(cplx<T> (&v)[32]
     }
 }
 
-// Outer stage of the split column transform, in place.  grid = (N / 256, M, batch), 256 threads = 256 adjacent
-// columns; otw[t * 32 + j] = exp(-2 pi i t j / N).  A CTA works on one t, so its 32 twiddles are staged in shared memory
+// Outer stage of the split column transform, in place.  grid = (N / THREADS, M, batch), one thread per column; otw[t * 32 + j] = exp(-2 pi i t j / N).  A CTA works on one t, so its 32 twiddles are staged in shared memory
 // once: as per-thread global loads they miss in an L1 that the streaming field keeps flushing, and the inverse stage, which
 // needs them before its butterfly, ran at 4.7 TB/s instead of 6.5 (tools/micro/outer_stage_probe.cu).  The field is read
 // and written exactly once per sweep: ld.cs / st.cs.
+// CTA shape: 256 threads x 2 per SM (complex64, 122-126 registers); complex128 holds its 32 values in 128 registers
+// (210-226 in all) and runs 64 threads x 4 per SM -- small CTAs whose load, butterfly and store phases interleave: column
+// pass at 8192^2 complex128 1251 / 1180 / 1150 us with 256 / 128 / 64 threads.
+template <typename T> struct OuterGeo { static constexpr int THREADS = sizeof(T) == 4 ? 256 : PA_OUTER_THREADS_F64; };
 template <typename T, int N, bool INV>
-__global__ void __launch_bounds__(256, sizeof(T) == 4 ? 2 : 1) k_col_outer(cplx<T>* __restrict__ field, const cplx<T>* __restrict__ otw) {
+__global__ void __launch_bounds__(OuterGeo<T>::THREADS, sizeof(T) == 4 ? 2 : 256 / OuterGeo<T>::THREADS)
+k_col_outer(cplx<T>* __restrict__ field, const cplx<T>* __restrict__ otw) {
     using C = cplx<T>;
     constexpr int R0 = 32, M = N / R0;
     __shared__ C sw[R0];
     const int t = blockIdx.y;
-    C* p = field + ((size_t)blockIdx.z * N + t) * N + blockIdx.x * 256 + threadIdx.x;
+    C* p = field + ((size_t)blockIdx.z * N + t) * N + blockIdx.x * OuterGeo<T>::THREADS + threadIdx.x;
     constexpr size_t STEP = (size_t)M * N;
     C v[32];
     if constexpr (!INV) {
