@@ -161,7 +161,7 @@ def run_reference(args):
         "stats_check": {"seeds": [1, len(etas)], "eta_first3": etas[:3], "mean_eta": float(np.mean(etas)),
                         "sem_eta": float(np.std(etas, ddof=1) / np.sqrt(len(etas))) if len(etas) > 1 else None},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -567,7 +567,7 @@ def run_c3(args):
                     "host_draw_ms_per_step": draw_ms, "value_with_predrawn_coefficients": world * args.steps * B / dt_pre},
             "roofline": roof, "roofline_screen": roof_screen, "cpu_baseline": cpu, "stats_check": stats,
         }
-        print(json.dumps(line))
+        emit(line)
     if comm is not None:
         comm.close()
     d.close()
@@ -619,7 +619,7 @@ def run_c4(args):
     digest = hashlib.sha1(np.ascontiguousarray(records).tobytes()).hexdigest()
     if d.rank == 0:
         value = total * args.steps / dt
-        print(json.dumps({
+        emit({
             "metric": METRIC + " through Simulation([BeamResult, PDTResult]).run()", "value": value, "unit": UNIT, "n_gpus": d.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
@@ -632,7 +632,7 @@ def run_c4(args):
             "statistics": {"sigma_bw": beam.bw, "sigma_lt": beam.lt, "w_st": beam.st, "mean_eta": float(np.mean(pdt.measures[0].data)),
                            "hist_nonzero_bins": int((hist > 0).sum()), "allreduced_statistics_equal_gathered": ok,
                            "records_sha1": digest},
-        }))
+        })
     assert ok, "all-reduced statistics differ from the statistics of the gathered records"
     d.close()
 
@@ -724,7 +724,7 @@ def run_c5(args):
         name = max(rl["per_kernel_us"], key=rl["per_kernel_us"].get)
         roof = dict(rl, kernel=name, achieved=rl["algorithmic_bytes_per_launch"] / rl["per_kernel_us"][name] / 1e3,
                     frac=rl["per_kernel_frac"][name], traffic=None)
-        print(json.dumps({
+        emit({
             "metric": "channel realizations/sec (8192^2, 20 screens, 100 km)", "value": c64["value"], "unit": UNIT, "n_gpus": d.world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": c64["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
@@ -733,11 +733,32 @@ def run_c5(args):
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roof,
             "complex64": c64, "complex128": out["complex128"],
             "complex64_vs_complex128_rel_l2": rel, "stated_tolerance_complex64_config5": 2.5e-5,
-        }))
+        })
     d.close()
 
 
+_REAL_STDOUT = None
+
+
+def keep_stdout_for_the_json_line():
+    """Everything any library writes to file descriptor 1 during the run (NCCL prints its version there when NCCL_DEBUG is
+    set) goes to stderr; emit() puts the one JSON line on the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
 def main():
+    keep_stdout_for_the_json_line()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)

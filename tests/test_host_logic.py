@@ -500,3 +500,27 @@ def test_every_symbol_of_the_scope_table_is_importable_under_the_reference_names
     g = importlib.import_module("pyatmosphere.grids").RectGrid((5, 8), 0.5)
     assert (g._left_bound, g._right_bound, g._top_bound, g._bottom_bound) == (-2, 3, -4, 4)       # grids.py:36-50
     assert list(g.extent) == [-1.0, 1.5, -2.0, 2.0]
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line(tmp_path):
+    """bench.py --impl reference (the CPU arm, runnable here): stdout carries ONE line and it parses; whatever else lands on
+    file descriptor 1 during the run (NCCL prints its version there when NCCL_DEBUG is set) is moved to stderr."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-samples", "1"], capture_output=True, text=True, timeout=600, cwd=str(tmp_path))
+    assert run.returncode == 0, run.stderr[-2000:]
+    lines = [l for l in run.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, run.stdout[:500]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["unit"] == "realizations/s" and line["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] == "port"
+
+    import bench
+    # the mechanism itself: a write to fd 1 after keep_stdout_for_the_json_line() does not reach the real stdout
+    code = ("import os, bench; bench.keep_stdout_for_the_json_line(); os.write(1, b'NCCL version x\\n'); "
+            "bench.emit({'ok': 1})")
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root)
+    assert run.stdout == '{"ok": 1}\n' and "NCCL version x" in run.stderr
