@@ -49,7 +49,7 @@ class PolarDiscreteFunction:
     value: Sequence[float]
 
 
-def _centred_transform(data, delta, scale, forward):
+def _centred_transform(data, scale, forward):
     """[N][N] or [batch][N][N] complex array (host or device) -> DeviceArray of the same shape; see pa_fft2c."""
     import numpy as np
 
@@ -63,7 +63,7 @@ def _centred_transform(data, delta, scale, forward):
     if t.ndim not in (2, 3) or t.shape[-1] != t.shape[-2]:
         raise ValueError("fft2 / ifft2 take square [N][N] (or [batch][N][N]) arrays")
     n = int(t.shape[-1])
-    ctx = eng.grid_context(RectGrid(n, float(delta)))
+    ctx = eng.grid_context(RectGrid(n, 1.0))          # the transform itself does not depend on the spacing: one context per N
     src = t.to(ctx.cdtype).reshape(-1, n, n).contiguous()
     out = torch.empty_like(src)
     nat.check(ctx.lib.pa_fft2c(ctx.handle, nat.ptr(src), nat.ptr(out), int(src.shape[0]), int(forward), float(scale),
@@ -73,11 +73,10 @@ def _centred_transform(data, delta, scale, forward):
 
 def fft2(x, delta):
     """utils.py:42-44: fftshift(fft2(fftshift(x))) * delta**2 (grid sizes are even, so fftshift == ifftshift)."""
-    return _centred_transform(x, delta, float(delta) ** 2, True)
+    return _centred_transform(x, float(delta) ** 2, True)
 
 
 def ifft2(x, delta):
     """utils.py:47-50: ifftshift(ifft2(ifftshift(x))) * (N * delta)**2 with numpy's 1/N**2 inside ifft2, i.e. the plain
-    sum times delta**2; `delta` is the frequency step, the spatial step of the context is 1 / (N * delta)."""
-    n = int(x.shape[-1])
-    return _centred_transform(x, 1.0 / (n * float(delta)), float(delta) ** 2, False)
+    sum times delta**2; `delta` is the frequency step."""
+    return _centred_transform(x, float(delta) ** 2, False)
