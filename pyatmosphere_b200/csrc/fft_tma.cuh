@@ -36,6 +36,16 @@ template <int N> struct ColSlots { static constexpr int value = N == 4096 ? 2 : 
 #ifndef PA_TMA_ROW_THREADS
 #define PA_TMA_ROW_THREADS 128      // row pass: small CTAs (one 2048-point row each), several per SM
 #endif
+#ifndef PA_TMA_ROW_TURNS
+#define PA_TMA_ROW_TURNS 1
+#endif
+#ifndef PA_TMA_ROW_SLOTS_8192
+#define PA_TMA_ROW_SLOTS_8192 2
+#endif
+// Row pass: three slots, or two for the 64 KiB rows of 8192^2 -- 192 KiB of shared memory would leave ~60 KiB of L1 for the
+// 61 KiB twiddle table of the first stage plus the streaming screen values; with two slots the refill of the idle slot is
+// issued in the middle of the next tile (as in the two-slot column ring).
+template <int N> struct RowSlots { static constexpr int value = N == 8192 ? PA_TMA_ROW_SLOTS_8192 : kSlots; };
 #ifndef PA_TMA_COL_BYTES
 #define PA_TMA_COL_BYTES 65536      // column pass: 64 KiB tiles (4 columns of 2048 complex64)
 #endif
@@ -51,7 +61,12 @@ template <typename T, int N, int E> struct TmaRowGeo {
     static constexpr int THREADS = FPB * TPF;
     static constexpr int SLOT = FPB * N * (int)sizeof(C);
     static constexpr int CHUNK = SLOT < 16384 ? SLOT : 16384;               // bytes per bulk copy
-    static constexpr int SMEM = kSlots * SLOT + 64;
+    static constexpr int SLOTS = RowSlots<N>::value;
+    // PA_TMA_ROW_TURNS: with a two-slot ring the screen values of a tile (FPB rows of N reals) travel through one more,
+    // single-buffered region instead of per-thread global loads
+    static constexpr int TSLOT = FPB * N * (int)sizeof(T);
+    static constexpr bool TURNS_STAGED = PA_TMA_ROW_TURNS && SLOTS == 2 && TSLOT % 16 == 0;
+    static constexpr int SMEM = SLOTS * SLOT + (TURNS_STAGED ? TSLOT : 0) + 64;
     static constexpr bool OK = THREADS <= 1024 && THREADS >= 32 && SMEM <= 227 * 1024 && SLOT % 16 == 0;
 };
 // geometry of the column pass: TC adjacent columns per tile
@@ -112,47 +127,73 @@ __global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArg
     using C = cplx<T>;
     using G = TmaRowGeo<T, N, E>;
     constexpr int TPF = G::TPF, FPB = G::FPB;
-    constexpr int kSlotBytes = G::SLOT;
+    constexpr int kSlotBytes = G::SLOT, RS = G::SLOTS;
     extern __shared__ __align__(1024) unsigned char smem_tma[];
     C* slots = reinterpret_cast<C*>(smem_tma);
     const uint32_t slot0 = ptx::smem_u32(smem_tma);
-    const uint32_t bar0 = slot0 + kSlots * kSlotBytes;
+    constexpr bool TS = G::TURNS_STAGED;
+    const uint32_t tslot = slot0 + RS * kSlotBytes;                           // screen rows of the current tile (TS)
+    const uint32_t bar0 = tslot + (TS ? G::TSLOT : 0);
+    const uint32_t tbar = bar0 + 8 * RS;
+    const T* tsm = reinterpret_cast<const T*>(smem_tma + RS * kSlotBytes);
     const int f = threadIdx.x / TPF, t = threadIdx.x % TPF;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kSlots; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        for (int s = 0; s < RS; ++s) ptx::mbar_init(bar0 + 8 * s, 1);
+        ptx::mbar_init(tbar, 1);
         ptx::fence_mbar_init();
     }
     __syncthreads();
+    auto issue_turns = [&](int k) {          // thread 0, after every thread has finished reading the previous tile's values
+        const int tile = blockIdx.x + k * gridDim.x;
+        if (!TS || a.turns == nullptr || tile >= ntiles) return;
+        ptx::mbar_expect_tx(tbar, G::TSLOT);
+        const char* src = reinterpret_cast<const char*>(a.turns) + (size_t)tile * G::TSLOT;
+        constexpr int TCH = G::TSLOT < 16384 ? G::TSLOT : 16384;
+#pragma unroll
+        for (int o = 0; o < G::TSLOT; o += TCH) ptx::bulk_g2s(tslot + o, src + o, TCH, tbar);
+    };
     auto issue_load = [&](int k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) return;
-        const int slot = k % kSlots;
+        const int slot = k % RS;
         ptx::mbar_expect_tx(bar0 + 8 * slot, kSlotBytes);
         const char* src = reinterpret_cast<const char*>(a.field) + (size_t)tile * kSlotBytes;
 #pragma unroll
         for (int o = 0; o < kSlotBytes; o += G::CHUNK) ptx::bulk_g2s(slot0 + slot * kSlotBytes + o, src + o, G::CHUNK, bar0 + 8 * slot);
-        if (a.turns != nullptr)      // pull the tile's screen rows towards L2 ahead of the compute threads
+        if (!TS && a.turns != nullptr)      // pull the tile's screen rows towards L2 ahead of the compute threads
             ptx::bulk_prefetch_l2(reinterpret_cast<const char*>(a.turns) + (size_t)tile * (kSlotBytes / 2), kSlotBytes / 2);
     };
     if (threadIdx.x == 0) {
         issue_load(0);
+        issue_turns(0);
         issue_load(1);
     }
     const RowAddr<N, E> addr{f * N};
     for (int k = 0;; ++k) {
         const int tile = blockIdx.x + k * gridDim.x;
         if (tile >= ntiles) break;
-        const int slot = k % kSlots;
+        const int slot = k % RS;
         C* sm = slots + (size_t)slot * (kSlotBytes / sizeof(C));
         const int row = tile * FPB + f;
-        ptx::mbar_wait(bar0 + 8 * slot, (k / kSlots) & 1);
+        ptx::mbar_wait(bar0 + 8 * slot, (k / RS) & 1);
         C v[E];
 #pragma unroll
         for (int i = 0; i < E; ++i) v[i] = sm[f * N + (IN_PERM ? io_pos<N, E>(t, i) : reg_pos<N, E, 0>(t, i))];
         __syncthreads();                                   // slot is now scratch for the exchanges
+        if constexpr (RS == 2) {
+            // two-slot ring: the other slot held tile k-1, whose store was committed at the end of the previous iteration
+            if (threadIdx.x == 0 && k >= 1) {
+                ptx::bulk_wait_read<0>();
+                issue_load(k + 1);
+            }
+        }
         if constexpr (IN_PERM) fft_inv<T, N, E>(v, t, sm, addr, a.tw);
         if (a.turns != nullptr) {
             const T* tr = a.turns + (size_t)row * N;
+            if constexpr (TS) {
+                ptx::mbar_wait(tbar, k & 1);
+                tr = tsm + (size_t)f * N;
+            }
 #pragma unroll
             for (int i = 0; i < E; ++i) {
                 C e = expm2pi(tr[reg_pos<N, E, 0>(t, i)]);
@@ -176,8 +217,11 @@ __global__ void __launch_bounds__(TmaRowGeo<T, N, E>::THREADS) k_rows_tma(RowArg
         if (threadIdx.x == 0) {
             ptx::bulk_s2g(reinterpret_cast<char*>(a.field) + (size_t)tile * kSlotBytes, slot0 + slot * kSlotBytes, kSlotBytes);
             ptx::bulk_commit();
-            ptx::bulk_wait_read<1>();                      // the store of tile k-1 has left its slot ...
-            issue_load(k + 2);                             // ... which is the slot of tile k+2
+            if constexpr (RS >= 3) {
+                ptx::bulk_wait_read<1>();                  // the store of tile k-1 has left its slot ...
+                issue_load(k + 2);                         // ... which is the slot of tile k+2
+            }
+            issue_turns(k + 1);                            // the barriers above: nobody reads this tile's screen values any more
         }
     }
     if (threadIdx.x == 0) ptx::bulk_wait_read<0>();

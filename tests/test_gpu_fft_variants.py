@@ -36,3 +36,44 @@ print("OK")
 def test_vacuum_leg_with_each_fft_variant(env):
     r = subprocess.run([sys.executable, "-c", SCRIPT % ROOT], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+
+
+TURB_SCRIPT = r"""
+import numpy as np, sys
+sys.path.insert(0, %r)
+import pyatmosphere_b200 as pa
+pa.gpu.config.update(use_gpu=True, dtype="complex64", screen_method="exact")
+n = 8192
+ch = pa.Channel(
+    grid=pa.RectGrid(n, 0.75e-3), source=pa.GaussianSource(wvl=808e-9, w0=0.12, F0=np.inf),
+    path=pa.IdenticalPhaseScreensPath(
+        phase_screen=pa.SSPhaseScreen(model=pa.MVKModel(Cn2=5e-16, l0=6e-3, L0=1e3),
+                                      f_grid=pa.RandLogPolarGrid(points=2**7, f_min=1 / 1e3 / 15, f_max=1 / 6e-3 * 2)),
+        length=30e3, count=3),
+    pupil=pa.CirclePupil(radius=0.2))
+np.random.seed(11)
+out = ch.run(pupil=False).get()
+np.save(sys.argv[1], out[::8, ::8].copy())
+crop = out[4096 - 64:4096 + 64, 4096 - 64:4096 + 64]
+np.save(sys.argv[1] + ".crop.npy", crop.copy())
+print("OK", float(np.sum(np.abs(out.astype(np.complex128)) ** 2) * 0.75e-3 ** 2))
+"""
+
+
+def test_turbulent_path_at_8192_agrees_between_the_two_row_kernels(tmp_path):
+    '''8192^2, three screens: the TMA-fed row pass (two-slot ring, screen rows staged through shared memory -- the default
+    there) and the direct-access row pass must produce the same field from the same numpy draws (the screens multiply the
+    field inside the row pass, so a screen row applied to the wrong field row would show here; unitarity alone would not).'''
+    import numpy as np
+    outs = {}
+    for name, env in (("tma", {"PYATM_FFT_ROWS_TMA": "1"}), ("direct", {"PYATM_FFT_ROWS_TMA": "0"})):
+        path = str(tmp_path / (name + ".npy"))
+        r = subprocess.run([sys.executable, "-c", TURB_SCRIPT % ROOT, path], env=dict(os.environ, **env), capture_output=True,
+                           text=True, timeout=900)
+        assert r.returncode == 0 and "OK" in r.stdout, r.stdout + r.stderr
+        outs[name] = (np.load(path).astype(np.complex128), np.load(path + ".crop.npy").astype(np.complex128))
+    for a, b in zip(outs["tma"], outs["direct"]):
+        err = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert err < 2e-6, err
+    # and the screens did something: the turbulent field is not the vacuum beam
+    assert np.abs(outs["tma"][1]).std() / np.abs(outs["tma"][1]).mean() > 0.05
