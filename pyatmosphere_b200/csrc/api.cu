@@ -93,7 +93,7 @@ struct pa_ctx {
     double* table = nullptr; size_t table_bytes = 0;
     std::vector<TensorMapEntry> tmaps;   // column-pass tensor maps, keyed by (field pointer, batch)
     bool use_tma = true;        // column pass: TMA-fed persistent kernel
-    bool rows_tma = false;      // row pass: the direct-access kernel is faster (smem-bound), TMA variant kept for experiments
+    bool rows_tma = false;      // row pass through the TMA-fed kernel: 8192^2 complex64 and complex128 at every size (fft_tma.cuh: RowSlots)
     double* rowsums = nullptr; size_t rowsums_bytes = 0;   // per-row sums of the fused final pass
     void* tcws = nullptr; size_t tcws_bytes = 0;          // fp16 operand blocks of the tensor-core screen path
     int* tc_err = nullptr;
@@ -591,7 +591,7 @@ int pa_ctx_create(pa_ctx** out, int device, int n, int precision) {
     c->use_tma = !direct;
     // row pass: the direct-access kernel everywhere except 8192^2 complex64, where one row is a whole 64 KiB tile and the
     // TMA-fed ring is a little ahead (473 against 484 us; at 2048^2 / 4096^2 it loses: 145 / 234 against 132 / 150)
-    c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") ? atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0 : (n == 8192 && precision == PA_C64);
+    c->rows_tma = getenv("PYATM_FFT_ROWS_TMA") ? atoi(getenv("PYATM_FFT_ROWS_TMA")) != 0 : ((n == 8192 && precision == PA_C64) || precision == PA_C128);
     c->sep_first_leg = !(getenv("PYATM_NO_ANALYTIC_LEG") && atoi(getenv("PYATM_NO_ANALYTIC_LEG")) != 0);
     *out = c;
     return PA_OK;

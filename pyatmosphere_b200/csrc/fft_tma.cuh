@@ -42,10 +42,13 @@ template <int N> struct ColSlots { static constexpr int value = N == 4096 ? 2 : 
 #ifndef PA_TMA_ROW_SLOTS_8192
 #define PA_TMA_ROW_SLOTS_8192 2
 #endif
-// Row pass: three slots, or two for the 64 KiB rows of 8192^2 -- 192 KiB of shared memory would leave ~60 KiB of L1 for the
-// 61 KiB twiddle table of the first stage plus the streaming screen values; with two slots the refill of the idle slot is
-// issued in the middle of the next tile (as in the two-slot column ring).
-template <int N> struct RowSlots { static constexpr int value = N == 8192 ? PA_TMA_ROW_SLOTS_8192 : kSlots; };
+// Row pass: three slots, or two + a staging region for the tile's screen rows (TmaRowGeo::TURNS_STAGED).  Two where the
+// direct-access kernel cannot hide its loads: the 64 KiB rows of 8192^2 (one 512-thread CTA per SM; 192 KiB of slots would
+// also leave the L1 too small for the 61 KiB twiddle table of the first stage) and complex128 at every size (us per pass,
+// direct -> two slots + staging: 1024^2 x 8: 113.7 -> 97.1, 2048^2 x 4: 238 -> 205, 4096^2: 248 -> 224).  complex64 below
+// 8192 keeps the direct kernel (131.5 against 146 at 2048^2).  With two slots the refill of the idle slot is issued in the
+// middle of the next tile (as in the two-slot column ring).
+template <typename T, int N> struct RowSlots { static constexpr int value = (N == 8192 || sizeof(T) == 8) ? PA_TMA_ROW_SLOTS_8192 : kSlots; };
 #ifndef PA_TMA_COL_BYTES
 #define PA_TMA_COL_BYTES 65536      // column pass: 64 KiB tiles (4 columns of 2048 complex64)
 #endif
@@ -61,7 +64,7 @@ template <typename T, int N, int E> struct TmaRowGeo {
     static constexpr int THREADS = FPB * TPF;
     static constexpr int SLOT = FPB * N * (int)sizeof(C);
     static constexpr int CHUNK = SLOT < 16384 ? SLOT : 16384;               // bytes per bulk copy
-    static constexpr int SLOTS = RowSlots<N>::value;
+    static constexpr int SLOTS = RowSlots<T, N>::value;
     // PA_TMA_ROW_TURNS: with a two-slot ring the screen values of a tile (FPB rows of N reals) travel through one more,
     // single-buffered region instead of per-thread global loads
     static constexpr int TSLOT = FPB * N * (int)sizeof(T);
